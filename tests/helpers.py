@@ -1,0 +1,61 @@
+"""Shared test helpers (CPU side).  The oracle is imported here as the checker only."""
+import os
+
+import numpy as np
+import torch
+
+from physdock_b200.synthetic import DiTDims, make_dit_state, make_complex, checksum
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+T_LEVELS = [4608.0, 100.0, 10.0, 1.0, 0.2]
+_cache = {}
+
+
+def load_npz(name):
+    if name not in _cache:
+        with np.load(os.path.join(GOLDEN, name)) as f:
+            _cache[name] = {k: f[k] for k in f.files}
+    return _cache[name]
+
+
+def T(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def medium_state():
+    if "sd" not in _cache:
+        dims = DiTDims.named("medium")
+        sd = make_dit_state(dims, seed=0)
+        _cache["sd"] = (dims, sd, checksum(torch.cat([v.flatten() for v in sd.values()])))
+    return _cache["sd"]
+
+
+def complex_64_512():
+    if "cx" not in _cache:
+        _cache["cx"] = make_complex(64, 512, DiTDims.named("medium"), seed=1)
+    return _cache["cx"]
+
+
+def dit_inputs_64_512():
+    """Regenerates the x_hat / t_hat sequence of oracle/make_golden.py section (ii)."""
+    g = torch.Generator().manual_seed(3)
+    out = []
+    for t in T_LEVELS:
+        x_hat = torch.randn(4, 512, 3, generator=g) * (t ** 2 + 100) ** 0.5
+        out.append((t, x_hat, torch.full([4], t)))
+    return out
+
+
+def rel_close(name, got, want, rtol, atol):
+    got, want = got.detach().double().cpu(), want.detach().double().cpu()
+    assert got.shape == want.shape, f"{name}: shape {tuple(got.shape)} != {tuple(want.shape)}"
+    err = (got - want).abs()
+    tol = atol + rtol * want.abs()
+    bad = err > tol
+    if bool(bad.any()):
+        idx = torch.nonzero(bad)[0].tolist()
+        raise AssertionError(
+            f"{name}: {int(bad.sum())}/{bad.numel()} off; max abs err {float(err.max()):.3e} "
+            f"(|want| max {float(want.abs().max()):.3e}); first bad at {idx}: got {float(got[tuple(idx)]):.6e} "
+            f"want {float(want[tuple(idx)]):.6e}")
+    return float(err.max())
