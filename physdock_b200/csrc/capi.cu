@@ -1,0 +1,419 @@
+// C ABI (include/physdock_b200.h): handle, workspace carve-up, the AF3DiT pipeline, op-level wrappers.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/physdock_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+using namespace pdk;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(const char* where, cudaError_t e) {
+    g_err = std::string(where) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+    return (int)e ? (int)e : -1;
+}
+int fail_msg(const char* where, const char* msg) {
+    g_err = std::string(where) + ": " + msg;
+    return -1;
+}
+#define PDK_TRY(where, expr)                          \
+    do {                                              \
+        cudaError_t _e = (expr);                      \
+        if (_e != cudaSuccess) return fail(where, _e); \
+    } while (0)
+
+inline int64_t pad128(int64_t n) { return (n + 127) / 128 * 128; }
+inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+inline const __half* H(const void* p) { return reinterpret_cast<const __half*>(p); }
+inline __half* H(void* p) { return reinterpret_cast<__half*>(p); }
+
+}  // namespace
+
+struct pdk_dit {
+    pdk_dit_dims d{};
+    pdk_dit_weights w{};
+    std::vector<pdk_block_weights> blocks;
+    bool have_weights = false;
+    // prepared complex
+    bool prepared = false;
+    const float* a = nullptr;
+    const float* s = nullptr;
+    const int32_t* tok_start = nullptr;
+    const int32_t* atom2tok = nullptr;
+    const float* bias_atom = nullptr;
+    const float* bias_tok = nullptr;
+    int64_t Na = 0, Nt = 0, Sa = 0, St = 0;   // Sa/St = padded lengths
+    int H_a() const { return (int)(d.c_a / kHeadDim); }
+    int H_s() const { return (int)(d.c_s / kHeadDim); }
+};
+
+namespace {
+
+struct Workspace {
+    float *coef, *tsilu, *mod, *ba, *bs, *down, *up;
+    __half *xh, *xl, *qh, *ql, *kh, *kl, *vh, *vl, *oh, *ol, *hh, *hl;
+    size_t bytes;
+};
+
+// Carves the scratch buffer.  base == nullptr just measures.
+Workspace carve(const pdk_dit& h, int64_t B, int64_t Sa, int64_t St, uint8_t* base) {
+    Workspace w{};
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        uint8_t* p = base ? base + off : nullptr;
+        off += align_up(bytes);
+        return p;
+    };
+    const size_t Ma = (size_t)B * Sa, Mt = (size_t)B * St;
+    const size_t act = std::max(Ma * h.d.c_a, Mt * h.d.c_s);            // elements of the widest activation
+    const size_t hid = std::max(Ma * h.d.hidden_a, Mt * h.d.hidden_s);
+    w.coef = (float*)take((size_t)B * 4 * 4);
+    w.tsilu = (float*)take((size_t)B * kTimeDim * 4);
+    w.mod = (float*)take((size_t)B * h.d.n_mod * 4);
+    w.ba = (float*)take(Ma * h.d.c_a * 4);
+    w.bs = (float*)take(Mt * h.d.c_s * 4);
+    w.down = (float*)take(Ma * h.d.c_s * 4);
+    w.up = (float*)take(Mt * h.d.c_a * 4);
+    __half** planes[] = {&w.xh, &w.xl, &w.qh, &w.ql, &w.kh, &w.kl, &w.vh, &w.vl, &w.oh, &w.ol};
+    for (auto pp : planes) *pp = (__half*)take(act * 2);
+    w.hh = (__half*)take(hid * 2);
+    w.hl = (__half*)take(hid * 2);
+    w.bytes = off;
+    return w;
+}
+
+constexpr int kLaunchesPerBlock = 7;
+
+// One DiTBlock (transformers.py:155-159): x += Attn(x); x += Transition(x).
+int run_block(const pdk_dit& h, const pdk_block_weights& bw, const Workspace& ws, float* x, int64_t B, int64_t Sp,
+              int c, int hidden, const float* bias, cudaStream_t st) {
+    const int M = (int)(B * Sp);
+    const int Hh = c / kHeadDim;
+    const int nmod = (int)h.d.n_mod;
+    const float eps = (float)h.d.eps;
+    // --- attention (attentions.py:240-265)
+    PDK_TRY("adaln(attn)", launch_adaln(x, ws.mod, nmod, (int)bw.mod_attn_off, ws.xh, ws.xl, (int)B, (int)Sp, c, eps, st));
+    GemmArgs g{};
+    g.Ah = ws.xh; g.Al = ws.xl; g.lda = c;
+    g.Wh = H(bw.wqkv_h); g.Wl = H(bw.wqkv_l); g.ldw = c;
+    g.M = M; g.N = 3 * c; g.K = c;
+    g.qh = ws.qh; g.ql = ws.ql; g.kh = ws.kh; g.kl = ws.kl; g.vh = ws.vh; g.vl = ws.vl;
+    g.norm_q = bw.norm_q; g.norm_k = bw.norm_k; g.c = c; g.rows_per_sample = (int)Sp;
+    g.rms_eps = eps; g.q_scale = kLog2e / sqrtf((float)kHeadDim);
+    PDK_TRY("gemm(qkv)", launch_gemm(EPI_QKV, g, st));
+    AttnArgs at{ws.qh, ws.ql, ws.kh, ws.kl, ws.vh, ws.vl, bias, ws.oh, ws.ol, (int)B, Hh, (int)Sp, c};
+    PDK_TRY("attention", launch_attention(at, st));
+    g = GemmArgs{};
+    g.Ah = ws.oh; g.Al = ws.ol; g.lda = c;
+    g.Wh = H(bw.wo_h); g.Wl = H(bw.wo_l); g.ldw = c;
+    g.M = M; g.N = c; g.K = c;
+    g.bias = bw.bo; g.out = x; g.ldo = c;
+    g.gate = ws.mod + bw.mod_attn_off + 2 * c; g.gate_stride = nmod; g.rows_per_sample = (int)Sp;
+    PDK_TRY("gemm(out)", launch_gemm(EPI_GATE_RESID, g, st));
+    // --- transition (transitions.py:21-30)
+    PDK_TRY("adaln(ffn)", launch_adaln(x, ws.mod, nmod, (int)bw.mod_ffn_off, ws.xh, ws.xl, (int)B, (int)Sp, c, eps, st));
+    g = GemmArgs{};
+    g.Ah = ws.xh; g.Al = ws.xl; g.lda = c;
+    g.Wh = H(bw.w13_h); g.Wl = H(bw.w13_l); g.ldw = c;
+    g.M = M; g.N = 2 * hidden; g.K = c;
+    g.ph = ws.hh; g.pl = ws.hl; g.ldp = hidden;
+    PDK_TRY("gemm(w13)", launch_gemm(EPI_SWIGLU, g, st));
+    g = GemmArgs{};
+    g.Ah = ws.hh; g.Al = ws.hl; g.lda = hidden;
+    g.Wh = H(bw.w2_h); g.Wl = H(bw.w2_l); g.ldw = hidden;
+    g.M = M; g.N = c; g.K = hidden;
+    g.out = x; g.ldo = c;
+    g.gate = ws.mod + bw.mod_ffn_off + 2 * c; g.gate_stride = nmod; g.rows_per_sample = (int)Sp;
+    PDK_TRY("gemm(w2)", launch_gemm(EPI_GATE_RESID, g, st));
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pdk_abi_version(void) { return PDK_ABI_VERSION; }
+const char* pdk_last_error(void) { return g_err.c_str(); }
+int64_t pdk_pad_len(int64_t n) { return pad128(n); }
+
+int pdk_dit_create(const pdk_dit_dims* dims, pdk_dit** out) {
+    if (!dims || !out) return fail_msg("pdk_dit_create", "null argument");
+    const pdk_dit_dims& d = *dims;
+    if (d.c_a != 128 || d.c_s != 512 || d.c_ap != 16 || d.c_z != 128)
+        return fail_msg("pdk_dit_create", "kernels are specialised for c_a=128, c_ap=16, c_s=512, c_z=128 (PhysDock/configs.py:59-63)");
+    if (d.hidden_a % 32 || d.hidden_s % 32 || d.hidden_a % 64 || d.hidden_s % 64)
+        return fail_msg("pdk_dit_create", "SwiGLU widths must be multiples of 64");
+    if (d.n_atom_blocks <= 0 || d.n_token_blocks <= 0 || d.n_mod <= 0 || d.n_mod % 4)
+        return fail_msg("pdk_dit_create", "bad block counts / n_mod");
+    pdk_dit* h = new (std::nothrow) pdk_dit();
+    if (!h) return fail_msg("pdk_dit_create", "out of host memory");
+    h->d = d;
+    *out = h;
+    return 0;
+}
+
+int pdk_dit_destroy(pdk_dit* h) {
+    delete h;
+    return 0;
+}
+
+int pdk_dit_set_weights(pdk_dit* h, const pdk_dit_weights* w) {
+    if (!h || !w || !w->blocks) return fail_msg("pdk_dit_set_weights", "null argument");
+    const int64_t want = 2 * h->d.n_atom_blocks + h->d.n_token_blocks;
+    if (w->n_blocks != want) return fail_msg("pdk_dit_set_weights", "n_blocks != 2*n_atom_blocks + n_token_blocks");
+    h->w = *w;
+    h->blocks.assign(w->blocks, w->blocks + w->n_blocks);
+    h->w.blocks = h->blocks.data();
+    h->have_weights = true;
+    return 0;
+}
+
+int pdk_dit_bias_bytes(const pdk_dit* h, int64_t Na, int64_t Nt, size_t* atom_bytes, size_t* token_bytes) {
+    if (!h || !atom_bytes || !token_bytes || Na <= 0 || Nt <= 0) return fail_msg("pdk_dit_bias_bytes", "bad argument");
+    const size_t Sa = pad128(Na), St = pad128(Nt);
+    *atom_bytes = (size_t)(2 * h->d.n_atom_blocks) * h->H_a() * Sa * Sa * 4;
+    *token_bytes = (size_t)h->d.n_token_blocks * h->H_s() * St * St * 4;
+    return 0;
+}
+
+int pdk_dit_workspace_bytes(const pdk_dit* h, int64_t B, int64_t Na, int64_t Nt, size_t* bytes) {
+    if (!h || !bytes || B <= 0 || Na <= 0 || Nt <= 0) return fail_msg("pdk_dit_workspace_bytes", "bad argument");
+    *bytes = carve(*h, B, pad128(Na), pad128(Nt), nullptr).bytes;
+    return 0;
+}
+
+int pdk_dit_prepare_complex(pdk_dit* h, const float* a, const float* ap, const float* s, const float* z,
+                            const float* ap_mask, const float* z_mask, const int32_t* tok_start,
+                            const int32_t* atom2tok, int64_t Na, int64_t Nt, float* bias_atom,
+                            float* bias_tok, void* stream) {
+    if (!h || !h->have_weights) return fail_msg("pdk_dit_prepare_complex", "weights not set");
+    if (!a || !ap || !s || !z || !ap_mask || !z_mask || !tok_start || !atom2tok || !bias_atom || !bias_tok)
+        return fail_msg("pdk_dit_prepare_complex", "null argument");
+    if (Na <= 0 || Nt <= 0) return fail_msg("pdk_dit_prepare_complex", "empty complex");
+    h->prepared = false;
+    const int64_t Sa = pad128(Na), St = pad128(Nt);
+    const int LHa = (int)(2 * h->d.n_atom_blocks) * h->H_a();
+    const int LHt = (int)h->d.n_token_blocks * h->H_s();
+    // nn.LayerNorm default eps (attentions.py:232 passes none)
+    PDK_TRY("pair_bias(atom)", launch_pair_bias(ap, ap_mask, h->w.wz_atom_T, h->w.bz_atom, bias_atom, (int)Na, (int)Sa,
+                                                (int)h->d.c_ap, LHa, 1e-5f, (float)h->d.inf, S(stream)));
+    PDK_TRY("pair_bias(token)", launch_pair_bias(z, z_mask, h->w.wz_tok_T, h->w.bz_tok, bias_tok, (int)Nt, (int)St,
+                                                 (int)h->d.c_z, LHt, 1e-5f, (float)h->d.inf, S(stream)));
+    h->a = a; h->s = s; h->tok_start = tok_start; h->atom2tok = atom2tok;
+    h->bias_atom = bias_atom; h->bias_tok = bias_tok;
+    h->Na = Na; h->Nt = Nt; h->Sa = Sa; h->St = St;
+    h->prepared = true;
+    return 0;
+}
+
+int64_t pdk_dit_launches_per_denoise(const pdk_dit* h) {
+    if (!h) return 0;
+    // time_embed, mod, precond | blocks | split, gemm(down), segmean | split, gemm(up), gather | denoise_out
+    return 3 + kLaunchesPerBlock * (2 * h->d.n_atom_blocks + h->d.n_token_blocks) + 3 + 3 + 1;
+}
+
+int pdk_dit_denoise(pdk_dit* h, const float* x_hat, const float* t_hat, int64_t B, void* workspace,
+                    size_t workspace_bytes, float* x_denoised, void* stream) {
+    if (!h || !h->prepared) return fail_msg("pdk_dit_denoise", "no prepared complex");
+    if (!x_hat || !t_hat || !workspace || !x_denoised || B <= 0) return fail_msg("pdk_dit_denoise", "bad argument");
+    const pdk_dit_dims& d = h->d;
+    const int64_t Sa = h->Sa, St = h->St;
+    Workspace ws = carve(*h, B, Sa, St, reinterpret_cast<uint8_t*>(workspace));
+    if (ws.bytes > workspace_bytes) return fail_msg("pdk_dit_denoise", "workspace too small");
+    cudaStream_t st = S(stream);
+    const int ca = (int)d.c_a, cs = (int)d.c_s;
+    const int Ha = h->H_a(), Hs = h->H_s();
+    const int nA = (int)d.n_atom_blocks, nT = (int)d.n_token_blocks;
+
+    // precond (transformers.py:218-226) + all AdaLN-Zero modulations of this step
+    PDK_TRY("time_embed", launch_time_embed(t_hat, h->w.freq, h->w.te_w1, h->w.te_b1, h->w.te_w2, h->w.te_b2,
+                                            (float)d.sigma_data, ws.tsilu, ws.coef, (int)B, st));
+    PDK_TRY("mod_gemv", launch_mod_gemv(ws.tsilu, h->w.wmod, h->w.bmod, ws.mod, (int)B, (int)d.n_mod, st));
+    PDK_TRY("precond", launch_precond(x_hat, ws.coef, h->a, h->w.wx, h->w.bx, ws.ba, (int)B, (int)h->Na, (int)Sa, ca, st));
+
+    // atom encoder (transformers.py:252)
+    const size_t plane_a = (size_t)Ha * Sa * Sa, plane_t = (size_t)Hs * St * St;
+    for (int l = 0; l < nA; ++l) {
+        int rc = run_block(*h, h->blocks[l], ws, ws.ba, B, Sa, ca, (int)d.hidden_a, h->bias_atom + l * plane_a, st);
+        if (rc) return rc;
+    }
+    // downscale (transformers.py:205-212)
+    PDK_TRY("split(ba)", launch_split(ws.ba, ws.xh, ws.xl, (size_t)B * Sa * ca, st));
+    {
+        GemmArgs g{};
+        g.Ah = ws.xh; g.Al = ws.xl; g.lda = ca;
+        g.Wh = H(h->w.wdown_h); g.Wl = H(h->w.wdown_l); g.ldw = ca;
+        g.M = (int)(B * Sa); g.N = cs; g.K = ca;
+        g.bias = h->w.bdown; g.act_silu = 1; g.out = ws.down; g.ldo = cs;
+        PDK_TRY("gemm(down)", launch_gemm(EPI_STORE, g, st));
+    }
+    PDK_TRY("segment_mean", launch_segment_mean(ws.down, h->tok_start, h->s, ws.bs, (int)B, (int)h->Nt, (int)Sa, (int)St, cs, st));
+    // token DiT (transformers.py:255)
+    for (int l = 0; l < nT; ++l) {
+        int rc = run_block(*h, h->blocks[nA + l], ws, ws.bs, B, St, cs, (int)d.hidden_s, h->bias_tok + l * plane_t, st);
+        if (rc) return rc;
+    }
+    // upscale (transformers.py:214-216)
+    PDK_TRY("split(bs)", launch_split(ws.bs, ws.xh, ws.xl, (size_t)B * St * cs, st));
+    {
+        GemmArgs g{};
+        g.Ah = ws.xh; g.Al = ws.xl; g.lda = cs;
+        g.Wh = H(h->w.wup_h); g.Wl = H(h->w.wup_l); g.ldw = cs;
+        g.M = (int)(B * St); g.N = ca; g.K = cs;
+        g.bias = h->w.bup; g.out = ws.up; g.ldo = ca;
+        PDK_TRY("gemm(up)", launch_gemm(EPI_STORE, g, st));
+    }
+    PDK_TRY("gather_add", launch_gather_add(ws.ba, ws.up, h->atom2tok, (int)B, (int)h->Na, (int)Sa, (int)St, ca, st));
+    // atom decoder (transformers.py:259)
+    for (int l = 0; l < nA; ++l) {
+        int rc = run_block(*h, h->blocks[nA + nT + l], ws, ws.ba, B, Sa, ca, (int)d.hidden_a,
+                           h->bias_atom + (size_t)(nA + l) * plane_a, st);
+        if (rc) return rc;
+    }
+    // denoise (transformers.py:228-233)
+    PDK_TRY("denoise_out", launch_denoise_out(ws.ba, x_hat, ws.coef, h->w.norm_r_w, h->w.norm_r_b, h->w.wr, x_denoised,
+                                              (int)B, (int)h->Na, (int)Sa, ca, (float)d.eps, st));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------- sampler ops
+int pdk_centre_augment(const float* x, const float* x_exists, const float* u4, const float* trans,
+                       const float* noise, float lambda, float noise_scale, float trans_scale, float* x_out,
+                       int64_t B, int64_t Na, void* stream) {
+    if (!x || !x_exists || !u4 || !trans || !x_out) return fail_msg("pdk_centre_augment", "null argument");
+    PDK_TRY("centre_augment", launch_centre_augment(x, x_exists, u4, trans, noise, lambda, noise_scale, trans_scale,
+                                                    x_out, (int)B, (int)Na, S(stream)));
+    return 0;
+}
+
+int pdk_euler_update(const float* x_hat, const float* x_den, const float* aligned, const float* w,
+                     const float* t_hat, float t_next, float eta, float* x_next, int64_t B, int64_t Na,
+                     void* stream) {
+    if (!x_hat || !x_den || !t_hat || !x_next) return fail_msg("pdk_euler_update", "null argument");
+    PDK_TRY("euler", launch_euler(x_hat, x_den, aligned, w, t_hat, t_next, eta, x_next, (int)B, (int)Na, S(stream)));
+    return 0;
+}
+
+int pdk_template_select(const float* x_den, const int32_t* lig_idx, const float* ref_dist, const float* ref_poses,
+                        float* eps, int64_t* used, float* batch_ref_pos, int64_t B, int64_t Na, int64_t n_lig,
+                        int64_t C, void* stream) {
+    if (!x_den || !lig_idx || !ref_dist || !ref_poses || !eps || !used || !batch_ref_pos)
+        return fail_msg("pdk_template_select", "null argument");
+    PDK_TRY("template_eps", launch_template_eps(x_den, lig_idx, ref_dist, eps, (int)B, (int)Na, (int)n_lig, (int)C, S(stream)));
+    PDK_TRY("template_pick", launch_template_pick(eps, ref_poses, lig_idx, used, batch_ref_pos, (int)B, (int)Na, (int)n_lig,
+                                                  (int)C, S(stream)));
+    return 0;
+}
+
+int pdk_rigid_align(const float* x_den, const float* x_exists, const float* x_gt, int gt_batched, const float* w,
+                    float* aligned, int64_t B, int64_t Na, void* stream) {
+    if (!x_den || !x_exists || !x_gt || !w || !aligned) return fail_msg("pdk_rigid_align", "null argument");
+    PDK_TRY("rigid_align", launch_rigid_align(x_den, x_exists, x_gt, gt_batched, w, aligned, (int)B, (int)Na, S(stream)));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------- op-level wrappers
+int pdk_op_pair_bias(const float* pair, const float* mask, const float* wfoldT, const float* bfold, float* bias,
+                     int64_t Sn, int64_t S_pad, int64_t C, int64_t LH, float ln_eps, float inf_, void* stream) {
+    PDK_TRY("pair_bias", launch_pair_bias(pair, mask, wfoldT, bfold, bias, (int)Sn, (int)S_pad, (int)C, (int)LH, ln_eps, inf_, S(stream)));
+    return 0;
+}
+int pdk_op_time_embed(const float* t_hat, const float* freq, const float* w1, const float* b1, const float* w2,
+                      const float* b2, float sigma_data, float* tsilu, float* coef, int64_t B, void* stream) {
+    PDK_TRY("time_embed", launch_time_embed(t_hat, freq, w1, b1, w2, b2, sigma_data, tsilu, coef, (int)B, S(stream)));
+    return 0;
+}
+int pdk_op_mod_gemv(const float* tsilu, const float* wmod, const float* bmod, float* mod, int64_t B, int64_t n_mod,
+                    void* stream) {
+    PDK_TRY("mod_gemv", launch_mod_gemv(tsilu, wmod, bmod, mod, (int)B, (int)n_mod, S(stream)));
+    return 0;
+}
+int pdk_op_adaln(const float* x, const float* mod, int64_t mod_stride, int64_t mod_off, void* xh, void* xl, int64_t B,
+                 int64_t S_pad, int64_t c, float eps, void* stream) {
+    PDK_TRY("adaln", launch_adaln(x, mod, (int)mod_stride, (int)mod_off, H(xh), H(xl), (int)B, (int)S_pad, (int)c, eps, S(stream)));
+    return 0;
+}
+int pdk_op_split(const float* x, void* xh, void* xl, int64_t n, void* stream) {
+    PDK_TRY("split", launch_split(x, H(xh), H(xl), (size_t)n, S(stream)));
+    return 0;
+}
+static GemmArgs base_args(const void* Ah, const void* Al, int64_t lda, const void* Wh, const void* Wl, int64_t ldw,
+                          int64_t M, int64_t N, int64_t K) {
+    GemmArgs g{};
+    g.Ah = H(Ah); g.Al = H(Al); g.lda = (int)lda;
+    g.Wh = H(Wh); g.Wl = H(Wl); g.ldw = (int)ldw;
+    g.M = (int)M; g.N = (int)N; g.K = (int)K;
+    return g;
+}
+int pdk_op_gemm_store(const void* Ah, const void* Al, int64_t lda, const void* Wh, const void* Wl, int64_t ldw,
+                      int64_t M, int64_t N, int64_t K, const float* bias, int act_silu, float* out, int64_t ldo,
+                      void* stream) {
+    GemmArgs g = base_args(Ah, Al, lda, Wh, Wl, ldw, M, N, K);
+    g.bias = bias; g.act_silu = act_silu; g.out = out; g.ldo = (int)ldo;
+    PDK_TRY("gemm_store", launch_gemm(EPI_STORE, g, S(stream)));
+    return 0;
+}
+int pdk_op_gemm_gate_resid(const void* Ah, const void* Al, int64_t lda, const void* Wh, const void* Wl, int64_t ldw,
+                           int64_t M, int64_t N, int64_t K, const float* bias, const float* gate, int64_t gate_stride,
+                           int64_t rows_per_sample, float* x, int64_t ldx, void* stream) {
+    GemmArgs g = base_args(Ah, Al, lda, Wh, Wl, ldw, M, N, K);
+    g.bias = bias; g.gate = gate; g.gate_stride = (int)gate_stride; g.rows_per_sample = (int)rows_per_sample;
+    g.out = x; g.ldo = (int)ldx;
+    PDK_TRY("gemm_gate_resid", launch_gemm(EPI_GATE_RESID, g, S(stream)));
+    return 0;
+}
+int pdk_op_gemm_swiglu(const void* Ah, const void* Al, int64_t lda, const void* Wh, const void* Wl, int64_t ldw,
+                       int64_t M, int64_t N, int64_t K, void* ph, void* pl, int64_t ldp, void* stream) {
+    GemmArgs g = base_args(Ah, Al, lda, Wh, Wl, ldw, M, N, K);
+    g.ph = H(ph); g.pl = H(pl); g.ldp = (int)ldp;
+    PDK_TRY("gemm_swiglu", launch_gemm(EPI_SWIGLU, g, S(stream)));
+    return 0;
+}
+int pdk_op_gemm_qkv(const void* Ah, const void* Al, int64_t lda, const void* Wh, const void* Wl, int64_t ldw, int64_t M,
+                    int64_t c, const float* norm_q, const float* norm_k, float rms_eps, float q_scale,
+                    int64_t rows_per_sample, void* qh, void* ql, void* kh, void* kl, void* vh, void* vl, void* stream) {
+    GemmArgs g = base_args(Ah, Al, lda, Wh, Wl, ldw, M, 3 * c, c);
+    g.norm_q = norm_q; g.norm_k = norm_k; g.c = (int)c; g.rms_eps = rms_eps; g.q_scale = q_scale;
+    g.rows_per_sample = (int)rows_per_sample;
+    g.qh = H(qh); g.ql = H(ql); g.kh = H(kh); g.kl = H(kl); g.vh = H(vh); g.vl = H(vl);
+    PDK_TRY("gemm_qkv", launch_gemm(EPI_QKV, g, S(stream)));
+    return 0;
+}
+int pdk_op_attention(const void* qh, const void* ql, const void* kh, const void* kl, const void* vh, const void* vl,
+                     const float* bias, void* oh, void* ol, int64_t B, int64_t Hh, int64_t S_pad, void* stream) {
+    AttnArgs a{H(qh), H(ql), H(kh), H(kl), H(vh), H(vl), bias, H(oh), H(ol), (int)B, (int)Hh, (int)S_pad, (int)(Hh * kHeadDim)};
+    PDK_TRY("attention", launch_attention(a, S(stream)));
+    return 0;
+}
+int pdk_op_precond(const float* x_hat, const float* coef, const float* a, const float* wx, const float* bx, float* ba,
+                   int64_t B, int64_t Na, int64_t S_pad, int64_t c_a, void* stream) {
+    PDK_TRY("precond", launch_precond(x_hat, coef, a, wx, bx, ba, (int)B, (int)Na, (int)S_pad, (int)c_a, S(stream)));
+    return 0;
+}
+int pdk_op_segment_mean(const float* h, const int32_t* tok_start, const float* s, float* bs, int64_t B, int64_t Nt,
+                        int64_t Sa_pad, int64_t St_pad, int64_t c_s, void* stream) {
+    PDK_TRY("segment_mean", launch_segment_mean(h, tok_start, s, bs, (int)B, (int)Nt, (int)Sa_pad, (int)St_pad, (int)c_s, S(stream)));
+    return 0;
+}
+int pdk_op_gather_add(float* ba, const float* up, const int32_t* atom2tok, int64_t B, int64_t Na, int64_t Sa_pad,
+                      int64_t St_pad, int64_t c_a, void* stream) {
+    PDK_TRY("gather_add", launch_gather_add(ba, up, atom2tok, (int)B, (int)Na, (int)Sa_pad, (int)St_pad, (int)c_a, S(stream)));
+    return 0;
+}
+int pdk_op_denoise_out(const float* ba, const float* x_hat, const float* coef, const float* ln_w, const float* ln_b,
+                       const float* wr, float* x_den, int64_t B, int64_t Na, int64_t S_pad, int64_t c_a, float eps,
+                       void* stream) {
+    PDK_TRY("denoise_out", launch_denoise_out(ba, x_hat, coef, ln_w, ln_b, wr, x_den, (int)B, (int)Na, (int)S_pad, (int)c_a, eps, S(stream)));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,88 @@
+// Shared device helpers for the physdock_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+#define PDK_DEV __device__ __forceinline__
+
+namespace pdk {
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kPadBias = -1.0e30f;     // bias of padded key columns: exp2(kPadBias - m) == 0, stays finite
+constexpr int   kHeadDim = 32;           // attentions.py:223 (c_hidden)
+constexpr int   kTimeDim = 256;          // timestep_embeddings.py:157
+
+PDK_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- async copies --------------------------------------------------------------------------
+PDK_DEV void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src));
+}
+PDK_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> PDK_DEV void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// ---- warp-level matrix fragments (legacy tensor path; see DESIGN.md "v1 kernels") -----------
+PDK_DEV void ldmatrix_x4(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+PDK_DEV void ldmatrix_x4_trans(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+// D(16x8,f32) += A(16x16,f16,row) * B(16x8,f16,col)
+PDK_DEV void mma_f16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// ---- split-fp16 number format ----------------------------------------------------------------
+// x (fp32) ~= hi + lo with hi = fp16(x), lo = fp16(x - hi): 22 significant bits.  A product a*b is
+// evaluated on the tensor cores as a_hi*b_hi + a_hi*b_lo + a_lo*b_hi with fp32 accumulation, which
+// tools/precision_probe.py shows is indistinguishable from fp32 at the 1e-3 Angstrom parity budget.
+constexpr float kHalfMax = 65504.f;
+PDK_DEV void split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    x0 = fminf(fmaxf(x0, -kHalfMax), kHalfMax);
+    x1 = fminf(fmaxf(x1, -kHalfMax), kHalfMax);
+    __half2 h = __floats2half2_rn(x0, x1);
+    float2 hf = __half22float2(h);
+    __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+    hi = *reinterpret_cast<uint32_t*>(&h);
+    lo = *reinterpret_cast<uint32_t*>(&l);
+}
+// same, for values known to lie in [0, 1] (softmax probabilities)
+PDK_DEV void split2_unit(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    __half2 h = __floats2half2_rn(x0, x1);
+    float2 hf = __half22float2(h);
+    __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+    hi = *reinterpret_cast<uint32_t*>(&h);
+    lo = *reinterpret_cast<uint32_t*>(&l);
+}
+
+// 64-byte-row tile (32 halves per row): 16-byte chunk c of row r lives at chunk c ^ ((r>>1)&3).
+// Makes both the cp.async fills and every 8-row ldmatrix phase bank-conflict free.
+PDK_DEV uint32_t swz64(int row, int chunk) { return (uint32_t)(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4)); }
+
+// ---- math --------------------------------------------------------------------------------------
+PDK_DEV float ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(y) : "f"(x));
+    return y;
+}
+PDK_DEV float silu(float x) { return x / (1.0f + expf(-x)); }
+
+PDK_DEV float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+PDK_DEV double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace pdk

@@ -1,0 +1,332 @@
+// Conditioning and glue kernels of the denoiser: everything in AF3DiT.forward that is not a big GEMM or
+// the attention core (reference PhysDock/models/layers/transformers.py:205-233 and the AdaLN-Zero path,
+// primitives/adaptive_layer_norm_zero.py:18-21).  All are HBM/latency bound: coalesced, vectorised,
+// warp-shuffle reductions, fp32 arithmetic in the reference's operation order.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace pdk {
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// precond scalars + TimestepEmbeddings (transformers.py:219-224, timestep_embeddings.py:35-86,127-166).
+// One CTA per sample.  The sinusoid argument t_hat*c_noise reaches ~6.5e3 rad, where a 1-ulp change of the
+// fp32 log moves the phase by ~4e-4 rad; log/sin/cos are therefore evaluated in fp64 and rounded once, which
+// reproduces a correctly rounded fp32 libm (the oracle's CPU path is within 1 ulp of that).
+__global__ void __launch_bounds__(256) time_embed_kernel(const float* __restrict__ t_hat,
+                                                         const float* __restrict__ freq,
+                                                         const float* __restrict__ w1, const float* __restrict__ b1,
+                                                         const float* __restrict__ w2, const float* __restrict__ b2,
+                                                         float sigma_data, float* __restrict__ tsilu,
+                                                         float* __restrict__ coef) {
+    __shared__ float proj[kTimeDim];
+    __shared__ float hid[kTimeDim];
+    const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const float t = t_hat[b];
+    const float sd2 = sigma_data * sigma_data;
+    const float t2 = t * t;
+    if (tid == 0) {
+        coef[4 * b + 0] = 1.0f / sqrtf(t2 + sd2);                      // c_in   (:219)
+        coef[4 * b + 1] = sd2 / (sd2 + t2);                            // c_skip (:229)
+        coef[4 * b + 2] = sigma_data * t / sqrtf(sd2 + t2);            // c_out  (:230)
+        coef[4 * b + 3] = t;
+    }
+    const float c_noise = (float)log((double)(t / sigma_data)) / 4.0f;  // (:220)
+    const float t_in = t * c_noise;                                     // (:223) sic
+    if (tid < 128) {
+        const float arg = t_in * freq[tid];
+        proj[tid] = (float)cos((double)arg);          // flip_sin_to_cos=True -> [cos | sin]
+        proj[128 + tid] = (float)sin((double)arg);
+    }
+    __syncthreads();
+    for (int o = warp; o < kTimeDim; o += 8) {        // linear_1 + SiLU
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc = fmaf(proj[lane + 32 * i], w1[(size_t)o * kTimeDim + lane + 32 * i], acc);
+        acc = warp_sum(acc);
+        if (lane == 0) hid[o] = silu(acc + b1[o]);
+    }
+    __syncthreads();
+    for (int o = warp; o < kTimeDim; o += 8) {        // linear_2, then the SiLU every AdaLN applies first
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc = fmaf(hid[lane + 32 * i], w2[(size_t)o * kTimeDim + lane + 32 * i], acc);
+        acc = warp_sum(acc);
+        if (lane == 0) tsilu[(size_t)b * kTimeDim + o] = silu(acc + b2[o]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// mod[b, n] = sum_k tsilu[b,k] * wmod[n,k] + bmod[n]: the 36 AdaLN-Zero `Linear(256 -> 3c)` of the model in
+// one weight-streaming pass (adaptive_layer_norm_zero.py:19).  Warp per output column, samples in registers.
+constexpr int MOD_BCHUNK = 16;
+__global__ void __launch_bounds__(256) mod_gemv_kernel(const float* __restrict__ tsilu,
+                                                       const float* __restrict__ wmod,
+                                                       const float* __restrict__ bmod, float* __restrict__ mod,
+                                                       int B, int Nmod) {
+    __shared__ float ts[MOD_BCHUNK][kTimeDim];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n = blockIdx.x * 8 + warp;
+    float w[8];
+    if (n < Nmod) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) w[i] = __ldg(wmod + (size_t)n * kTimeDim + lane + 32 * i);
+    }
+    for (int b0 = 0; b0 < B; b0 += MOD_BCHUNK) {
+        const int nb = min(MOD_BCHUNK, B - b0);
+        __syncthreads();
+        for (int i = tid; i < nb * kTimeDim; i += 256) ts[i / kTimeDim][i % kTimeDim] = tsilu[(size_t)b0 * kTimeDim + i];
+        __syncthreads();
+        if (n < Nmod) {
+            for (int bb = 0; bb < nb; ++bb) {
+                float acc = 0.f;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc = fmaf(ts[bb][lane + 32 * i], w[i], acc);
+                acc = warp_sum(acc);
+                if (lane == 0) mod[(size_t)(b0 + bb) * Nmod + n] = acc + bmod[n];
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// AdaLN-Zero modulate: planes = split( LN_noaffine(x) * (1 + scale) + shift )   (adaptive_layer_norm_zero.py:20)
+// Warp per row; C/32 values per lane held in registers (C = 128 or 512).
+template <int C>
+__global__ void __launch_bounds__(256) adaln_kernel(const float* __restrict__ x, const float* __restrict__ mod,
+                                                    int mod_stride, int mod_off, __half* __restrict__ xh,
+                                                    __half* __restrict__ xl, int rows, int S_pad, float eps) {
+    constexpr int V = C / 128;     // float4 per lane
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float4* src = reinterpret_cast<const float4*>(x + (size_t)row * C);
+    float4 v[V];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        v[i] = src[lane + 32 * i];
+        sum += v[i].x + v[i].y + v[i].z + v[i].w;
+    }
+    const float mean = warp_sum(sum) * (1.f / C);
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+        sq += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum(sq) * (1.f / C) + eps);
+    const float* shift = mod + (size_t)(row / S_pad) * mod_stride + mod_off;
+    const float* scale = shift + C;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        const int c0 = 4 * (lane + 32 * i);
+        const float4 sh = *reinterpret_cast<const float4*>(shift + c0);
+        const float4 sc = *reinterpret_cast<const float4*>(scale + c0);
+        const float y0 = v[i].x * rstd * (1.f + sc.x) + sh.x;
+        const float y1 = v[i].y * rstd * (1.f + sc.y) + sh.y;
+        const float y2 = v[i].z * rstd * (1.f + sc.z) + sh.z;
+        const float y3 = v[i].w * rstd * (1.f + sc.w) + sh.w;
+        uint2 hi, lo;
+        split2(y0, y1, hi.x, lo.x);
+        split2(y2, y3, hi.y, lo.y);
+        *reinterpret_cast<uint2*>(xh + (size_t)row * C + c0) = hi;
+        *reinterpret_cast<uint2*>(xl + (size_t)row * C + c0) = lo;
+    }
+}
+
+__global__ void __launch_bounds__(256) split_kernel(const float* __restrict__ x, __half* __restrict__ xh,
+                                                    __half* __restrict__ xl, size_t n4) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 v = reinterpret_cast<const float4*>(x)[i];
+        uint2 hi, lo;
+        split2(v.x, v.y, hi.x, lo.x);
+        split2(v.z, v.w, hi.y, lo.y);
+        reinterpret_cast<uint2*>(xh)[i] = hi;
+        reinterpret_cast<uint2*>(xl)[i] = lo;
+    }
+}
+
+// ba = Linear_{3->c_a}(x_hat * c_in) + a   (transformers.py:222); pad rows zeroed.
+__global__ void __launch_bounds__(256) precond_kernel(const float* __restrict__ x_hat, const float* __restrict__ coef,
+                                                      const float* __restrict__ a, const float* __restrict__ wx,
+                                                      const float* __restrict__ bx, float* __restrict__ ba, int B,
+                                                      int Na, int S_pad, int c_a) {
+    const int per_row = c_a / 4;
+    const size_t total = (size_t)B * S_pad * per_row;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int c4 = (int)(i % per_row);
+        const size_t r = i / per_row;
+        const int s = (int)(r % S_pad), b = (int)(r / S_pad);
+        float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (s < Na) {
+            const float c_in = coef[4 * b];
+            const float* xp = x_hat + ((size_t)b * Na + s) * 3;
+            const float x0 = xp[0] * c_in, x1 = xp[1] * c_in, x2 = xp[2] * c_in;
+            const float4 av = *reinterpret_cast<const float4*>(a + (size_t)s * c_a + 4 * c4);
+            const float4 bv = *reinterpret_cast<const float4*>(bx + 4 * c4);
+            const float* w = wx + (size_t)(4 * c4) * 3;
+            out.x = fmaf(x2, w[2], fmaf(x1, w[1], x0 * w[0])) + bv.x + av.x;
+            out.y = fmaf(x2, w[5], fmaf(x1, w[4], x0 * w[3])) + bv.y + av.y;
+            out.z = fmaf(x2, w[8], fmaf(x1, w[7], x0 * w[6])) + bv.z + av.z;
+            out.w = fmaf(x2, w[11], fmaf(x1, w[10], x0 * w[9])) + bv.w + av.w;
+        }
+        reinterpret_cast<float4*>(ba)[i] = out;
+    }
+}
+
+// Token pooling of AF3DiT.downscale (transformers.py:207-212).  The reference forms per-token sums as a
+// difference of an fp32 cumsum over all atoms; summing each contiguous chunk directly is the same quantity
+// without the cancellation (documented deviation, ~1e-6 relative).
+__global__ void __launch_bounds__(256) segment_mean_kernel(const float* __restrict__ h, const int* __restrict__ tok_start,
+                                                           const float* __restrict__ s, float* __restrict__ bs, int B,
+                                                           int Nt, int Sa_pad, int St_pad, int c_s) {
+    const int per_row = c_s / 4;
+    const size_t total = (size_t)B * St_pad * per_row;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int c4 = (int)(i % per_row);
+        const size_t r = i / per_row;
+        const int tok = (int)(r % St_pad), b = (int)(r / St_pad);
+        float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (tok < Nt) {
+            const int a0 = tok_start[tok], a1 = tok_start[tok + 1];
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4* src = reinterpret_cast<const float4*>(h + ((size_t)b * Sa_pad) * c_s) + c4;
+            for (int at = a0; at < a1; ++at) {
+                const float4 v = src[(size_t)at * per_row];
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
+            const float den = (float)(a1 - a0) + 1e-3f;
+            const float4 sv = *reinterpret_cast<const float4*>(s + (size_t)tok * c_s + 4 * c4);
+            out.x = acc.x / den + sv.x; out.y = acc.y / den + sv.y;
+            out.z = acc.z / den + sv.z; out.w = acc.w / den + sv.w;
+        }
+        reinterpret_cast<float4*>(bs)[i] = out;
+    }
+}
+
+// AF3DiT.upscale (transformers.py:214-216): ba[b,i,:] += up[b, atom_id_to_token_id[i], :]
+__global__ void __launch_bounds__(256) gather_add_kernel(float* __restrict__ ba, const float* __restrict__ up,
+                                                         const int* __restrict__ atom2tok, int B, int Na, int Sa_pad,
+                                                         int St_pad, int c_a) {
+    const int per_row = c_a / 4;
+    const size_t total = (size_t)B * Na * per_row;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int c4 = (int)(i % per_row);
+        const size_t r = i / per_row;
+        const int at = (int)(r % Na), b = (int)(r / Na);
+        const int tok = atom2tok[at];
+        float4* dst = reinterpret_cast<float4*>(ba + ((size_t)b * Sa_pad + at) * c_a) + c4;
+        const float4 u = *(reinterpret_cast<const float4*>(up + ((size_t)b * St_pad + tok) * c_a) + c4);
+        float4 v = *dst;
+        v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+        *dst = v;
+    }
+}
+
+// AF3DiT.denoise (transformers.py:228-233): x_den = c_skip x_hat + c_out Linear_{c_a->3}(LN_affine(ba)).
+// Warp per atom row (c_a = 128: one float4 per lane).
+__global__ void __launch_bounds__(256) denoise_out_kernel(const float* __restrict__ ba, const float* __restrict__ x_hat,
+                                                          const float* __restrict__ coef, const float* __restrict__ ln_w,
+                                                          const float* __restrict__ ln_b, const float* __restrict__ wr,
+                                                          float* __restrict__ x_den, int B, int Na, int S_pad,
+                                                          float eps) {
+    const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= B * Na) return;
+    const int b = r / Na, s = r % Na;
+    float4 v = reinterpret_cast<const float4*>(ba + ((size_t)b * S_pad + s) * 128)[lane];
+    const float mean = warp_sum(v.x + v.y + v.z + v.w) * (1.f / 128.f);
+    v.x -= mean; v.y -= mean; v.z -= mean; v.w -= mean;
+    const float rstd = 1.0f / sqrtf(warp_sum(v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w) * (1.f / 128.f) + eps);
+    const float4 g = reinterpret_cast<const float4*>(ln_w)[lane];
+    const float4 be = reinterpret_cast<const float4*>(ln_b)[lane];
+    const float y0 = v.x * rstd * g.x + be.x, y1 = v.y * rstd * g.y + be.y;
+    const float y2 = v.z * rstd * g.z + be.z, y3 = v.w * rstd * g.w + be.w;
+    float out[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const float4 w = reinterpret_cast<const float4*>(wr + j * 128)[lane];
+        out[j] = warp_sum(fmaf(y3, w.w, fmaf(y2, w.z, fmaf(y1, w.y, y0 * w.x))));
+    }
+    if (lane < 3) {
+        const float c_skip = coef[4 * b + 1], c_out = coef[4 * b + 2];
+        const float r_j = lane == 0 ? out[0] : (lane == 1 ? out[1] : out[2]);
+        const size_t o = ((size_t)b * Na + s) * 3 + lane;
+        x_den[o] = __fadd_rn(__fmul_rn(c_skip, x_hat[o]), __fmul_rn(c_out, r_j));
+    }
+}
+
+inline int grid_for(size_t n, int block = 256, int cap = 148 * 16) {
+    size_t g = (n + block - 1) / block;
+    return (int)(g < (size_t)cap ? (g ? g : 1) : cap);
+}
+
+}  // namespace
+
+cudaError_t launch_time_embed(const float* t_hat, const float* freq, const float* w1, const float* b1,
+                              const float* w2, const float* b2, float sigma_data, float* tsilu, float* coef,
+                              int B, cudaStream_t st) {
+    if (B <= 0) return cudaErrorInvalidValue;
+    time_embed_kernel<<<B, 256, 0, st>>>(t_hat, freq, w1, b1, w2, b2, sigma_data, tsilu, coef);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_mod_gemv(const float* tsilu, const float* wmod, const float* bmod, float* mod, int B,
+                            int Nmod, cudaStream_t st) {
+    if (B <= 0 || Nmod <= 0) return cudaErrorInvalidValue;
+    mod_gemv_kernel<<<(Nmod + 7) / 8, 256, 0, st>>>(tsilu, wmod, bmod, mod, B, Nmod);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_adaln(const float* x, const float* mod, int mod_stride, int mod_off, __half* xh, __half* xl,
+                         int B, int S_pad, int c, float eps, cudaStream_t st) {
+    const int rows = B * S_pad;
+    if (rows <= 0 || (mod_off % 4) || (mod_stride % 4)) return cudaErrorInvalidValue;
+    if (c == 128)
+        adaln_kernel<128><<<(rows + 7) / 8, 256, 0, st>>>(x, mod, mod_stride, mod_off, xh, xl, rows, S_pad, eps);
+    else if (c == 512)
+        adaln_kernel<512><<<(rows + 7) / 8, 256, 0, st>>>(x, mod, mod_stride, mod_off, xh, xl, rows, S_pad, eps);
+    else
+        return cudaErrorInvalidValue;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_split(const float* x, __half* xh, __half* xl, size_t n, cudaStream_t st) {
+    if (n == 0 || n % 4) return cudaErrorInvalidValue;
+    split_kernel<<<grid_for(n / 4), 256, 0, st>>>(x, xh, xl, n / 4);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_precond(const float* x_hat, const float* coef, const float* a, const float* wx, const float* bx,
+                           float* ba, int B, int Na, int S_pad, int c_a, cudaStream_t st) {
+    if (c_a % 4 || Na > S_pad) return cudaErrorInvalidValue;
+    precond_kernel<<<grid_for((size_t)B * S_pad * (c_a / 4)), 256, 0, st>>>(x_hat, coef, a, wx, bx, ba, B, Na, S_pad, c_a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_segment_mean(const float* h, const int* tok_start, const float* s, float* bs, int B, int Nt,
+                                int Sa_pad, int St_pad, int c_s, cudaStream_t st) {
+    if (c_s % 4 || Nt > St_pad) return cudaErrorInvalidValue;
+    segment_mean_kernel<<<grid_for((size_t)B * St_pad * (c_s / 4)), 256, 0, st>>>(h, tok_start, s, bs, B, Nt, Sa_pad,
+                                                                               St_pad, c_s);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_gather_add(float* ba, const float* up, const int* atom2tok, int B, int Na, int Sa_pad,
+                              int St_pad, int c_a, cudaStream_t st) {
+    if (c_a % 4) return cudaErrorInvalidValue;
+    gather_add_kernel<<<grid_for((size_t)B * Na * (c_a / 4)), 256, 0, st>>>(ba, up, atom2tok, B, Na, Sa_pad, St_pad, c_a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_denoise_out(const float* ba, const float* x_hat, const float* coef, const float* ln_w,
+                               const float* ln_b, const float* wr, float* x_den, int B, int Na, int S_pad,
+                               int c_a, float eps, cudaStream_t st) {
+    if (c_a != 128) return cudaErrorInvalidValue;
+    denoise_out_kernel<<<(B * Na + 7) / 8, 256, 0, st>>>(ba, x_hat, coef, ln_w, ln_b, wr, x_den, B, Na, S_pad, eps);
+    return cudaGetLastError();
+}
+
+}  // namespace pdk

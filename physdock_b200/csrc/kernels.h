@@ -1,0 +1,96 @@
+// Internal launcher declarations shared by the kernels and the C ABI (capi.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+namespace pdk {
+
+// ----------------------------------------------------------------------------- split-fp16 GEMM
+// C[M,N] = A[M,K] * W[N,K]^T with A, W given as (hi, lo) fp16 planes; fp32 accumulation of
+// Ah*Wh + Ah*Wl + Al*Wh.  M % 128 == 0, N % 128 == 0, K % 32 == 0 (activations are padded to S_pad).
+enum GemmEpilogue {
+    EPI_STORE = 0,       // out[M,N] (fp32) = act(acc + bias)
+    EPI_GATE_RESID = 1,  // out[M,N] (fp32, in place) += (acc + bias) * gate[sample(row)][col]
+    EPI_SWIGLU = 2,      // W rows interleaved in blocks of 8 (w1 | w3): planes[M, N/2] = split(silu(h1) * h3)
+    EPI_QKV = 3,         // N = 3c: per-head RMSNorm on q and k, q pre-scaled, planes [B,H,S_pad,32]
+};
+
+struct GemmArgs {
+    const __half* Ah; const __half* Al; int lda;
+    const __half* Wh; const __half* Wl; int ldw;
+    int M, N, K;
+    const float* bias;          // [N] or nullptr
+    float* out; int ldo;        // EPI_STORE / EPI_GATE_RESID
+    int act_silu;               // EPI_STORE only
+    const float* gate;          // EPI_GATE_RESID: gate[sample * gate_stride + col]
+    int gate_stride;
+    int rows_per_sample;        // S_pad (EPI_GATE_RESID, EPI_QKV)
+    __half* ph; __half* pl; int ldp;   // EPI_SWIGLU output planes [M, N/2]
+    __half* qh; __half* ql; __half* kh; __half* kl; __half* vh; __half* vl;   // EPI_QKV
+    const float* norm_q; const float* norm_k;   // [32] RMSNorm gains
+    int c;                      // model width (N == 3c)
+    float rms_eps; float q_scale;
+};
+cudaError_t launch_gemm(GemmEpilogue epi, const GemmArgs& a, cudaStream_t st);
+
+// ----------------------------------------------------------------------------- pair-bias attention
+// q,k,v planes [B,H,S_pad,32] (q pre-scaled by log2e/sqrt(32)); bias [H,S_pad,S_pad] fp32 (pre-scaled by
+// log2e, pad columns = kPadBias); output planes o[B*S_pad, c] with column h*32+d.
+struct AttnArgs {
+    const __half* qh; const __half* ql; const __half* kh; const __half* kl; const __half* vh; const __half* vl;
+    const float* bias;
+    __half* oh; __half* ol;
+    int B, H, S_pad, c;
+};
+cudaError_t launch_attention(const AttnArgs& a, cudaStream_t st);
+
+// ----------------------------------------------------------------------------- pair-bias prepass
+// bias[l][h][i][j] = log2e * ( sum_c wfold[l*H+h][c] * xhat(pair[i][j])[c] + bfold[l*H+h] + (mask==0 ? -inf_ : 0) )
+// for i,j < S; pad columns kPadBias; pad rows 0.   pair [S,S,C] fp32, C in {16,128}, LH = L*H outputs per pair.
+cudaError_t launch_pair_bias(const float* pair, const float* mask, const float* wfold, const float* bfold,
+                             float* bias, int S, int S_pad, int C, int LH, float ln_eps, float inf_,
+                             cudaStream_t st);
+
+// ----------------------------------------------------------------------------- conditioning / glue
+// t_hat[B] -> tsilu[B,256] = SiLU(time_embedder(t_hat * c_noise)), coef[B,4] = (c_in, c_skip, c_out, t_hat)
+cudaError_t launch_time_embed(const float* t_hat, const float* freq, const float* w1, const float* b1,
+                              const float* w2, const float* b2, float sigma_data, float* tsilu, float* coef,
+                              int B, cudaStream_t st);
+// mod[B,Nmod] = tsilu[B,256] * wmod[Nmod,256]^T + bmod   (all AdaLN-Zero linears of the model at once)
+cudaError_t launch_mod_gemv(const float* tsilu, const float* wmod, const float* bmod, float* mod, int B,
+                            int Nmod, cudaStream_t st);
+// x[B*S_pad, c] -> planes: LN_noaffine(x) * (1 + scale) + shift, (shift, scale) = mod[b, off .. off+2c)
+cudaError_t launch_adaln(const float* x, const float* mod, int mod_stride, int mod_off, __half* xh, __half* xl,
+                         int B, int S_pad, int c, float eps, cudaStream_t st);
+// x[rows, c] fp32 -> planes
+cudaError_t launch_split(const float* x, __half* xh, __half* xl, size_t n, cudaStream_t st);
+// ba[B,S_pad,c_a] = W_x (x_hat * c_in) + b_x + a   (rows >= Na zeroed)
+cudaError_t launch_precond(const float* x_hat, const float* coef, const float* a, const float* wx, const float* bx,
+                           float* ba, int B, int Na, int S_pad, int c_a, cudaStream_t st);
+// bs[B,St_pad,c_s] = segment_sum(h[B,Sa_pad,c_s]) / (n + 1e-3) + s   (rows >= Nt zeroed)
+cudaError_t launch_segment_mean(const float* h, const int* tok_start, const float* s, float* bs, int B, int Nt,
+                                int Sa_pad, int St_pad, int c_s, cudaStream_t st);
+// ba[b, i, :] += up[b, atom2tok[i], :]
+cudaError_t launch_gather_add(float* ba, const float* up, const int* atom2tok, int B, int Na, int Sa_pad,
+                              int St_pad, int c_a, cudaStream_t st);
+// x_den = c_skip * x_hat + c_out * W_r LN(ba)
+cudaError_t launch_denoise_out(const float* ba, const float* x_hat, const float* coef, const float* ln_w,
+                               const float* ln_b, const float* wr, float* x_den, int B, int Na, int S_pad,
+                               int c_a, float eps, cudaStream_t st);
+
+// ----------------------------------------------------------------------------- coordinates / physics
+cudaError_t launch_centre_augment(const float* x, const float* x_exists, const float* u4, const float* trans,
+                                  const float* noise, float lambda, float noise_scale, float trans_scale,
+                                  float* x_out, int B, int Na, cudaStream_t st);
+cudaError_t launch_euler(const float* x_hat, const float* x_den, const float* aligned, const float* w,
+                         const float* t_hat, float t_next, float eta, float* x_next, int B, int Na,
+                         cudaStream_t st);
+cudaError_t launch_template_eps(const float* x_den, const int* lig_idx, const float* ref_dist, float* eps,
+                                int B, int Na, int n_lig, int C, cudaStream_t st);
+cudaError_t launch_template_pick(const float* eps, const float* ref_poses, const int* lig_idx, int64_t* used,
+                                 float* batch_ref_pos, int B, int Na, int n_lig, int C, cudaStream_t st);
+cudaError_t launch_rigid_align(const float* x_pred, const float* x_exists, const float* x_gt, int gt_batched,
+                               const float* w, float* aligned, int B, int Na, cudaStream_t st);
+
+}  // namespace pdk

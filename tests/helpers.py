@@ -58,4 +58,20 @@ def rel_close(name, got, want, rtol, atol):
             f"{name}: {int(bad.sum())}/{bad.numel()} off; max abs err {float(err.max()):.3e} "
             f"(|want| max {float(want.abs().max()):.3e}); first bad at {idx}: got {float(got[tuple(idx)]):.6e} "
             f"want {float(want[tuple(idx)]):.6e}")
+    _log(name, float(err.max()), float(tol.min()), float(want.abs().max()))
     return float(err.max())
+
+
+def _log(name, err, tol, scale):
+    """Appends (name, max error, tolerance, |want| max) to gpurun_out/parity_log.txt so tolerances can be audited."""
+    d = os.path.join(os.path.dirname(GOLDEN.rstrip("/")), "..", "gpurun_out")
+    try:
+        os.makedirs(d, exist_ok=True)
+        with open(os.path.join(d, "parity_log.txt"), "a") as f:
+            f.write(f"{name}\terr={err:.3e}\ttol={tol:.3e}\tscale={scale:.3e}\n")
+    except OSError:
+        pass
+
+
+def log_value(name, value):
+    _log(name, float(value), float("nan"), float("nan"))

@@ -1,0 +1,97 @@
+"""GPU parity of the whole denoiser (AF3DiT.forward) through the drop-in module B200DiT."""
+import pytest
+import torch
+
+from oracle import physdock_oracle as O
+from physdock_b200.synthetic import DiTDims, make_complex
+from tests.helpers import T, load_npz, medium_state, complex_64_512, dit_inputs_64_512, log_value
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+TOL_A = 1e-3      # Angstrom RMSD, the north-star budget (BASELINE.json)
+
+
+@pytest.fixture(scope="module")
+def dit():
+    from physdock_b200.dit import B200DiT
+    dims, sd, _ = medium_state()
+    return B200DiT.from_state_dict(sd, dims, device=DEV)
+
+
+def to_dev(cx):
+    return {k: v.to(DEV) for k, v in cx.items()}
+
+
+def test_denoiser_matches_reference_golden_64_512(dit):
+    """Outputs of the REAL reference AF3DiT (tests/golden/dit_64_512.npz) at 5 noise levels."""
+    cx = to_dev(complex_64_512())
+    g = load_npz("dit_64_512.npz")
+    for t, x_hat, t_hat in dit_inputs_64_512():
+        y = dit(cx, x_hat.to(DEV), t_hat.to(DEV), cx["a"], cx["ap"], cx["s"], cx["z"]).cpu()
+        r = float(O.rmsd(y, T(g[f"x_denoised_{t}"])).max())
+        r64 = float(O.rmsd(y, T(g[f"x_denoised_fp64_{t}"])).max())
+        log_value(f"dit64/512 t={t} rmsd_vs_ref_fp32", r)
+        log_value(f"dit64/512 t={t} rmsd_vs_ref_fp64", r64)
+        assert r < TOL_A, (t, r)
+        assert torch.isfinite(y).all()
+
+
+def test_denoiser_ragged_masked_complex_vs_oracle(dit):
+    """Ragged chunk sizes, zero-size tokens, masked atoms/tokens, sizes far from tile multiples."""
+    dims, sd, _ = medium_state()
+    for (Nt, Na, seed) in ((24, 100, 9), (40, 333, 10)):
+        cx = make_complex(Nt, Na, dims, seed=seed, ragged=True, mask_holes=True)
+        g = torch.Generator().manual_seed(seed)
+        x_hat = torch.randn(3, Na, 3, generator=g) * 30
+        t_hat = torch.tensor([300.0, 5.0, 0.1])
+        with torch.no_grad():
+            want = O.af3dit_forward(sd, cx, x_hat, t_hat, cx["a"], cx["ap"], cx["s"], cx["z"])
+        d = to_dev(cx)
+        got = dit(d, x_hat.to(DEV), t_hat.to(DEV), d["a"], d["ap"], d["s"], d["z"]).cpu()
+        # atoms that are masked out everywhere attend uniformly in the reference and are never used downstream
+        live = cx["a_mask"].bool()
+        r = float(O.rmsd(got[:, live], want[:, live]).max())
+        log_value(f"dit ragged {Nt}/{Na} rmsd", r)
+        assert r < TOL_A, (Nt, Na, r)
+
+
+def test_denoiser_256_2048_vs_oracle(dit):
+    """The benchmark shape (BASELINE.json configs[1]) against the CPU oracle, B=2."""
+    dims, sd, _ = medium_state()
+    cx = make_complex(256, 2048, dims, seed=1)
+    g = torch.Generator().manual_seed(5)
+    x_hat = torch.randn(2, 2048, 3, generator=g) * 50
+    t_hat = torch.tensor([40.0, 0.5])
+    with torch.no_grad():
+        want = O.af3dit_forward(sd, cx, x_hat, t_hat, cx["a"], cx["ap"], cx["s"], cx["z"])
+    d = to_dev(cx)
+    got = dit(d, x_hat.to(DEV), t_hat.to(DEV), d["a"], d["ap"], d["s"], d["z"]).cpu()
+    r = float(O.rmsd(got, want).max())
+    log_value("dit256/2048 rmsd", r)
+    assert r < TOL_A, r
+
+
+def test_dropin_contract_and_caching(dit):
+    """forward() has AF3DiT's signature; the per-complex cache is keyed on the conditioning tensors."""
+    cx = to_dev(complex_64_512())
+    x_hat = torch.randn(2, 512, 3, device=DEV) * 10
+    t_hat = torch.full([2], 3.0, device=DEV)
+    y1 = dit(cx, x_hat, t_hat, cx["a"], cx["ap"], cx["s"], cx["z"])
+    keep = dit._complex_keep
+    y2 = dit(batch=cx, x_hat=x_hat, t_hat=t_hat, a=cx["a"], ap=cx["ap"], s=cx["s"], z=cx["z"])
+    assert dit._complex_keep is keep, "second call must reuse the cached pair bias"
+    assert torch.equal(y1, y2), "denoiser must be deterministic"
+    # samples are independent: evaluating sample 1 alone gives the same bits
+    y_single = dit(cx, x_hat[1:], t_hat[1:], cx["a"], cx["ap"], cx["s"], cx["z"])
+    assert torch.equal(y_single[0], y1[1])
+    cx["ap"].mul_(1.0001)          # in-place edit bumps the version counter -> cache must refresh
+    y3 = dit(cx, x_hat, t_hat, cx["a"], cx["ap"], cx["s"], cx["z"])
+    assert dit._complex_keep is not keep
+    assert not torch.equal(y3, y1)
+
+
+def test_cpu_tensors_fail_loudly(dit):
+    from physdock_b200._lib import PdkError
+    cx = complex_64_512()
+    with pytest.raises(PdkError):
+        dit(cx, torch.zeros(1, 512, 3), torch.ones(1), cx["a"], cx["ap"], cx["s"], cx["z"])

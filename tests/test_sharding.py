@@ -1,0 +1,59 @@
+"""Host-side multi-GPU logic on CPU: world_size-2 gloo processes."""
+import os
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from physdock_b200.sharding import ShardedRNG, gather_samples, shard_range
+
+
+def test_shard_range_covers_all_samples():
+    for n in (1, 5, 16, 40, 41):
+        for ws in (1, 2, 3, 8):
+            spans = [shard_range(n, r, ws) for r in range(ws)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+
+
+class _CpuRNG:
+    def rand(self, shape):
+        return torch.rand(list(shape))
+
+    def normal(self, shape):
+        return torch.normal(0, 1, size=tuple(shape))
+
+
+def _worker(rank, ws, port, q):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=ws)
+    n = 5                                    # ragged: 3 + 2
+    lo, hi = shard_range(n, rank, ws)
+    torch.manual_seed(42)
+    rng = ShardedRNG(_CpuRNG(), n, rank, ws)
+    x0 = rng.normal((hi - lo, 7, 3))         # the per-rank slice of one global draw
+    u = rng.rand((hi - lo,))
+    local = x0 * 2 + u[:, None, None]        # stand-in for the per-sample computation
+    full = gather_samples(local)
+    if rank == 0:
+        q.put(full)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gather_equals_single_process():
+    ws, port = 2, 29571
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, ws, port, q)) for r in range(ws)]
+    for p in procs:
+        p.start()
+    full = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    torch.manual_seed(42)
+    x0 = torch.normal(0, 1, size=(5, 7, 3))
+    u = torch.rand([5])
+    assert torch.equal(full, x0 * 2 + u[:, None, None])
