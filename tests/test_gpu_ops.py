@@ -45,9 +45,11 @@ def test_gemm_store_vs_fp64(M, N, K):
     assert float((ops.planes_to_float(ah, al) - A).abs().max()) <= 3e-7 * float(A.abs().max())
     got = ops.gemm_store(ah, al, wh, wl, bias)
     want = (A.double() @ W.double().t() + bias.double())
-    rel_close("gemm_store", got, want, rtol=0, atol=2e-6 * float(want.abs().max()))
+    # split-fp16 operand error (2^-22) + fp32 accumulation over K terms
+    atol = (2e-6 + 2e-7 * math.sqrt(K)) * float(want.abs().max())
+    rel_close("gemm_store", got, want, rtol=0, atol=atol)
     got = ops.gemm_store(ah, al, wh, wl, None, silu=True)
-    rel_close("gemm_store+silu", got, F.silu(A.double() @ W.double().t()), rtol=0, atol=2e-6 * float(want.abs().max()))
+    rel_close("gemm_store+silu", got, F.silu(A.double() @ W.double().t()), rtol=0, atol=atol)
 
 
 @pytest.mark.parametrize("B,H,S", [(1, 4, 128), (2, 4, 384), (2, 16, 256)])
