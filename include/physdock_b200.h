@@ -47,7 +47,7 @@ typedef struct {          /* PhysDock/configs.py:59-88 ("dit" section) */
 typedef struct {          /* one DiTBlock (transformers.py:149-159); all device pointers */
     const void* wqkv_h; const void* wqkv_l;   /* fp16 [3c, c]: linear_q | linear_k | linear_v rows   (attentions.py:234-236) */
     const void* wo_h;   const void* wo_l;     /* fp16 [c, c]   linear_o                             (attentions.py:240) */
-    const void* w13_h;  const void* w13_l;    /* fp16 [2*hidden, c]: w1/w3 rows interleaved in blocks of 8 (feed_forward.py:26-28) */
+    const void* w13_h;  const void* w13_l;    /* fp16 [2*hidden, c]: w1/w3 rows interleaved in blocks of 16 (feed_forward.py:26-28) */
     const void* w2_h;   const void* w2_l;     /* fp16 [c, hidden] */
     const float* bo;                          /* [c] */
     const float* norm_q; const float* norm_k; /* [32] RMSNorm gains (attentions.py:238-239) */

@@ -1,0 +1,224 @@
+// Split-fp16 GEMM on the 5th-gen tensor cores: TMA -> smem ring -> tcgen05.mma (TMEM accumulator) -> fused epilogue.
+//
+// Replaces every `Linear.forward -> F.linear` call site on the hot path (reference
+// PhysDock/models/primitives/linear.py:146-161): q/k/v projections (attentions.py:248-250), out projection
+// (:263), SwiGLU w1/w3/w2 (feed_forward.py:30-31), linear_downscale/upscale (layers/transformers.py:206,215).
+//
+// C[M,N] = A[M,K] W[N,K]^T with A, W stored as (hi, lo) fp16 planes; per K=16 slice three MMAs
+// (Al*Wh + Ah*Wl + Ah*Wh) accumulate in fp32 in TMEM.
+//
+// CTA = one 128x128 output tile, 192 threads, warp-specialised:
+//   warp 0   : TMA producer (one lane): 4 plane tiles [128 rows x 32 halves] per stage, SWIZZLE_64B
+//   warp 1   : TMEM allocator + MMA issuer (one lane): 6 x tcgen05.mma.kind::f16 M128 N128 K16 per stage
+//   warps 2-5: epilogue; warp w owns TMEM lanes 32*(w%4)..+31, i.e. each THREAD owns one output row and reads
+//              32 consecutive accumulator columns per tcgen05.ld -- exactly one attention head / one SwiGLU
+//              column block, so the per-head RMSNorm and the SwiGLU product need no cross-thread traffic.
+// 3-stage ring (96 KB) + 128 TMEM columns => 2 CTAs per SM, so one CTA's epilogue overlaps the other's main loop.
+#include "common.cuh"
+#include "kernels.h"
+#include "umma.cuh"
+
+namespace pdk {
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 32, STAGES = 3;
+constexpr int TILE_BYTES = 128 * BK * 2;            // 8 KB: one fp16 plane tile, 64-byte rows
+constexpr int STAGE_BYTES = 4 * TILE_BYTES;         // A_hi, A_lo, W_hi, W_lo
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;   // + slack to 1024-align the ring
+constexpr int NTHREADS = 192;
+constexpr uint32_t TMEM_COLS = 128;
+
+PDK_DEV void store8(float* dst, const float (&v)[32]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        reinterpret_cast<float4*>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(NTHREADS, 2)
+gemm_umma_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUtensorMap mAl,
+                 const __grid_constant__ CUtensorMap mWh, const __grid_constant__ CUtensorMap mWl, const GemmArgs p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bars[2 * STAGES + 1];
+    __shared__ uint32_t tmem_slot;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int KT = p.K / BK;
+    const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar0 = smem_u32(&bars[0]);
+    auto full = [&](int s) { return bar0 + 8u * s; };
+    auto empty = [&](int s) { return bar0 + 8u * (STAGES + s); };
+    const uint32_t tfull = bar0 + 8u * (2 * STAGES);
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+        mbar_init(tfull, 1);
+        mbar_fence_init();
+        tma_prefetch_desc(&mAh); tma_prefetch_desc(&mAl); tma_prefetch_desc(&mWh); tma_prefetch_desc(&mWl);
+    }
+    if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kt = 0; kt < KT; ++kt) {
+                const int s = kt % STAGES;
+                const uint32_t ph = (uint32_t)(kt / STAGES) & 1u;
+                mbar_wait(empty(s), ph ^ 1u);
+                mbar_expect_tx(full(s), STAGE_BYTES);
+                const uint32_t dst = ring + s * STAGE_BYTES;
+                tma_load_2d(dst, &mAh, full(s), kt * BK, m0);
+                tma_load_2d(dst + TILE_BYTES, &mAl, full(s), kt * BK, m0);
+                tma_load_2d(dst + 2 * TILE_BYTES, &mWh, full(s), kt * BK, n0);
+                tma_load_2d(dst + 3 * TILE_BYTES, &mWl, full(s), kt * BK, n0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_f16(BM, BN);
+            for (int kt = 0; kt < KT; ++kt) {
+                const int s = kt % STAGES;
+                const uint32_t ph = (uint32_t)(kt / STAGES) & 1u;
+                mbar_wait(full(s), ph);
+                tc_fence_after();
+                const uint32_t src = ring + s * STAGE_BYTES;
+                const uint64_t ah = smem_desc(src, 512, kLayoutSw64), al = smem_desc(src + TILE_BYTES, 512, kLayoutSw64);
+                const uint64_t wh = smem_desc(src + 2 * TILE_BYTES, 512, kLayoutSw64);
+                const uint64_t wl = smem_desc(src + 3 * TILE_BYTES, 512, kLayoutSw64);
+#pragma unroll
+                for (int ks = 0; ks < BK / 16; ++ks) {
+                    const uint64_t o = (uint64_t)(ks * 2);                  // +32 bytes (>>4) per K=16 slice
+                    umma_f16(tmem, al + o, wh + o, idesc, (kt | ks) != 0);   // small terms first
+                    umma_f16(tmem, ah + o, wl + o, idesc, 1u);
+                    umma_f16(tmem, ah + o, wh + o, idesc, 1u);
+                }
+                umma_commit(empty(s));      // frees the smem stage once these MMAs have read it
+            }
+            umma_commit(tfull);             // accumulator complete
+        }
+    } else {
+        // ---------------------------------------------------------------- epilogue (128 threads = 128 rows)
+        mbar_wait(tfull, 0);
+        tc_fence_after();
+        const int q = warp & 3;
+        const int row = m0 + q * 32 + lane;
+        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+        for (int ch = 0; ch < BN / 32; ++ch) {
+            uint32_t raw[32];
+            tmem_ld32(taddr + ch * 32, raw);
+            tmem_ld_wait();
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+            const int col = n0 + ch * 32;
+            if constexpr (EPI == EPI_STORE) {
+                if (p.bias) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] += __ldg(p.bias + col + i);
+                }
+                if (p.act_silu) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = silu(v[i]);
+                }
+                store8(p.out + (size_t)row * p.ldo + col, v);
+            } else if constexpr (EPI == EPI_GATE_RESID) {
+                const float* gate = p.gate + (size_t)(row / p.rows_per_sample) * p.gate_stride + col;
+                float* x = p.out + (size_t)row * p.ldo + col;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float4 xv = reinterpret_cast<float4*>(x)[i];
+                    const float4 gv = __ldg(reinterpret_cast<const float4*>(gate) + i);
+                    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + col) + i);
+                    xv.x += (v[4 * i] + bv.x) * gv.x;
+                    xv.y += (v[4 * i + 1] + bv.y) * gv.y;
+                    xv.z += (v[4 * i + 2] + bv.z) * gv.z;
+                    xv.w += (v[4 * i + 3] + bv.w) * gv.w;
+                    reinterpret_cast<float4*>(x)[i] = xv;
+                }
+            } else if constexpr (EPI == EPI_SWIGLU) {
+                // W rows interleaved in blocks of 16: columns [0,16) = w1 rows, [16,32) = w3 rows of hidden j0..j0+15
+                const int j0 = col / 2;
+                uint32_t hi[8], lo[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    split2(silu(v[2 * i]) * v[16 + 2 * i], silu(v[2 * i + 1]) * v[16 + 2 * i + 1], hi[i], lo[i]);
+                uint4* dh = reinterpret_cast<uint4*>(p.ph + (size_t)row * p.ldp + j0);
+                uint4* dl = reinterpret_cast<uint4*>(p.pl + (size_t)row * p.ldp + j0);
+                dh[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]); dh[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+                dl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]); dl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+            } else {   // EPI_QKV: this chunk is one head of q, k or v
+                const int which = col / p.c;
+                const int head = (col % p.c) / kHeadDim;
+                const int H = p.c / kHeadDim;
+                if (which < 2) {    // per-head RMSNorm (rms_norm.py:14-19); q additionally carries log2e/sqrt(32)
+                    float ss = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) ss = fmaf(v[i], v[i], ss);
+                    const float inv = (1.0f / sqrtf(ss * (1.0f / kHeadDim) + p.rms_eps)) * (which == 0 ? p.q_scale : 1.0f);
+                    const float* gain = which == 0 ? p.norm_q : p.norm_k;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = v[i] * inv * __ldg(gain + i);
+                }
+                __half* dh = which == 0 ? p.qh : (which == 1 ? p.kh : p.vh);
+                __half* dl = which == 0 ? p.ql : (which == 1 ? p.kl : p.vl);
+                const size_t d0 = ((size_t)((row / p.rows_per_sample) * H + head) * p.rows_per_sample +
+                                   (row % p.rows_per_sample)) * kHeadDim;
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) split2(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    reinterpret_cast<uint4*>(dh + d0)[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+                    reinterpret_cast<uint4*>(dl + d0)[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, TMEM_COLS);
+}
+
+template <int EPI>
+cudaError_t launch_one(const GemmArgs& a, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_umma_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    CUtensorMap mAh, mAl, mWh, mWl;
+    cudaError_t e;
+    if ((e = get_tensor_map_f16(a.Ah, a.M, a.K, a.lda, BM, BK, 64, &mAh)) != cudaSuccess) return e;
+    if ((e = get_tensor_map_f16(a.Al, a.M, a.K, a.lda, BM, BK, 64, &mAl)) != cudaSuccess) return e;
+    if ((e = get_tensor_map_f16(a.Wh, a.N, a.K, a.ldw, BN, BK, 64, &mWh)) != cudaSuccess) return e;
+    if ((e = get_tensor_map_f16(a.Wl, a.N, a.K, a.ldw, BN, BK, 64, &mWl)) != cudaSuccess) return e;
+    dim3 grid(a.N / BN, a.M / BM);
+    gemm_umma_kernel<EPI><<<grid, NTHREADS, SMEM_BYTES, st>>>(mAh, mAl, mWh, mWl, a);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_gemm(GemmEpilogue epi, const GemmArgs& a, cudaStream_t st) {
+    if (a.M <= 0 || a.N <= 0 || a.K <= 0 || a.M % BM || a.N % BN || a.K % BK) return cudaErrorInvalidValue;
+    if (a.lda % 8 || a.ldw % 8) return cudaErrorInvalidValue;   // 16-byte global strides for TMA
+    switch (epi) {
+        case EPI_STORE: return launch_one<EPI_STORE>(a, st);
+        case EPI_GATE_RESID: return launch_one<EPI_GATE_RESID>(a, st);
+        case EPI_SWIGLU: return launch_one<EPI_SWIGLU>(a, st);
+        case EPI_QKV:
+            if (a.N != 3 * a.c || a.c % BN) return cudaErrorInvalidValue;
+            return launch_one<EPI_QKV>(a, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace pdk

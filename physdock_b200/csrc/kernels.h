@@ -12,7 +12,7 @@ namespace pdk {
 enum GemmEpilogue {
     EPI_STORE = 0,       // out[M,N] (fp32) = act(acc + bias)
     EPI_GATE_RESID = 1,  // out[M,N] (fp32, in place) += (acc + bias) * gate[sample(row)][col]
-    EPI_SWIGLU = 2,      // W rows interleaved in blocks of 8 (w1 | w3): planes[M, N/2] = split(silu(h1) * h3)
+    EPI_SWIGLU = 2,      // W rows interleaved in blocks of 16 (w1 | w3): planes[M, N/2] = split(silu(h1) * h3)
     EPI_QKV = 3,         // N = 3c: per-head RMSNorm on q and k, q pre-scaled, planes [B,H,S_pad,32]
 };
 

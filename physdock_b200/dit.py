@@ -8,7 +8,7 @@ runs in the hand-written sm_100a kernels behind include/physdock_b200.h:
     model.dit = B200DiT.from_reference(model.dit)        # the whole drop-in
 
 What is cached and when:
-  * weights  -> re-laid-out once per parameter version (`_pack`): q|k|v concatenated, w1/w3 interleaved,
+  * weights  -> re-laid-out once per parameter version (`_pack`): q|k|v concatenated, w1/w3 interleaved in blocks of 16,
     every matrix split into fp16 hi/lo planes, all 36 AdaLN-Zero linears concatenated, LayerNorm(z) affine
     folded into linear_z.
   * complex  -> `prepare_complex` runs once per (a, ap, s, z, masks): the pair-bias of every block
@@ -36,10 +36,11 @@ def _split_planes(w: torch.Tensor):
     return hi.contiguous(), lo.contiguous()
 
 
-def _interleave8(w1: torch.Tensor, w3: torch.Tensor) -> torch.Tensor:
-    """[hid,c],[hid,c] -> [2*hid,c] with rows in blocks of 8: w1[0:8], w3[0:8], w1[8:16], ..."""
+def _interleave16(w1: torch.Tensor, w3: torch.Tensor) -> torch.Tensor:
+    """[hid,c],[hid,c] -> [2*hid,c] with rows in blocks of 16: w1[0:16], w3[0:16], w1[16:32], ... so that one
+    32-column accumulator chunk of the GEMM epilogue holds h1 and h3 of the same 16 hidden channels."""
     hid, c = w1.shape
-    return torch.stack([w1.reshape(hid // 8, 8, c), w3.reshape(hid // 8, 8, c)], dim=1).reshape(2 * hid, c)
+    return torch.stack([w1.reshape(hid // 16, 16, c), w3.reshape(hid // 16, 16, c)], dim=1).reshape(2 * hid, c)
 
 
 class B200DiT(nn.Module):
@@ -165,7 +166,7 @@ class B200DiT(nn.Module):
             t["wqkv_h"], t["wqkv_l"] = _split_planes(torch.cat([sd[a + "linear_q.weight"], sd[a + "linear_k.weight"],
                                                                 sd[a + "linear_v.weight"]], 0))
             t["wo_h"], t["wo_l"] = _split_planes(sd[a + "linear_o.weight"])
-            t["w13_h"], t["w13_l"] = _split_planes(_interleave8(sd[f + "w1.weight"], sd[f + "w3.weight"]))
+            t["w13_h"], t["w13_l"] = _split_planes(_interleave16(sd[f + "w1.weight"], sd[f + "w3.weight"]))
             t["w2_h"], t["w2_l"] = _split_planes(sd[f + "w2.weight"])
             t["bo"] = sd[a + "linear_o.bias"].contiguous()
             t["norm_q"], t["norm_k"] = sd[a + "norm_q.weight"].contiguous(), sd[a + "norm_k.weight"].contiguous()
