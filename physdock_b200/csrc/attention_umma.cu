@@ -1,0 +1,326 @@
+// Dense pair-biased attention on tcgen05 / TMEM / TMA  (replaces F.scaled_dot_product_attention(q,k,v,attn_bias)
+// in DiTAttention, reference PhysDock/models/primitives/attentions.py:259-260).
+//
+// softmax(q k^T / sqrt(32) + bias) v with a dense fp32 bias [H,S,S] shared by all samples.  q (pre-scaled) and
+// bias arrive multiplied by log2(e): the softmax runs on exp2.  All operands are split-fp16 planes.
+//
+// CTA = (head h, 128 query rows, a group of up to 4 samples).  The samples of a group share every bias tile: it
+// is TMA-loaded once per key tile and read by all of them from shared memory, which divides the dominant L2
+// stream (bias, 4 B per score) by the group size.  Work unit u = (key tile j of 64 keys, sample g).
+//
+//   warp 8  TMA producer   : Q planes of the group (once); per key tile the bias tile [128 x 64] fp32 (two
+//                            SWIZZLE_128B boxes, double buffered) and per unit K_hi,K_lo,V_hi,V_lo [64 x 32] fp16
+//                            (SWIZZLE_64B, 6-stage ring)
+//   warp 9  MMA issuer     : S_g = Q_g K^T   (SS, M128 N64 K16 x 2 slices x 3 split products) into TMEM buffer g
+//                            O_g += P_g V    (TS: P from TMEM, V MN-major from smem; 4 slices x 3 products)
+//   warps 0-3 / 4-7        : two softmax warpgroups (samples g even / odd).  Thread = one query row: reads its 64
+//                            scores with tcgen05.ld, adds the bias row, row max / exp2 / row sum entirely in
+//                            registers (no shuffles), splits P into fp16 hi/lo and writes it back over S with
+//                            tcgen05.st (S and P alias).  O is rescaled lazily (only when the row max grows by
+//                            more than 2^8), directly in TMEM.
+// TMEM: 4 x 64 columns S/P + 4 x 32 columns O.  MMAs of one thread execute in issue order, which is what makes
+// the S/P aliasing and the accumulator reuse safe without extra barriers.
+#include "common.cuh"
+#include "kernels.h"
+#include "umma.cuh"
+
+namespace pdk {
+
+namespace {
+
+constexpr int G = 4;                 // samples per CTA
+constexpr int BQ = 128, BKV = 64, D = kHeadDim;
+constexpr int NS = 6;                // K/V ring stages
+constexpr int Q_PLANE = BQ * D * 2;                  // 8 KB
+constexpr int KV_PLANE = BKV * D * 2;                // 4 KB
+constexpr int KV_STAGE = 4 * KV_PLANE;               // 16 KB
+constexpr int BIAS_HALF = BQ * 32 * 4;               // 16 KB: [128 rows][32 fp32]
+constexpr int BIAS_TILE = 2 * BIAS_HALF;             // 32 KB
+constexpr int OFF_Q = 0;
+constexpr int OFF_BIAS = G * 2 * Q_PLANE;            // 64 KB
+constexpr int OFF_KV = OFF_BIAS + 2 * BIAS_TILE;     // 128 KB
+constexpr int SMEM_BYTES = OFF_KV + NS * KV_STAGE + 1024;   // 225 KB
+constexpr int NTHREADS = 320;
+constexpr uint32_t TMEM_COLS = 512;
+constexpr uint32_t COL_S = 0, COL_O = 256;
+constexpr float kRescaleThreshold = 8.0f;            // log2 domain: P <= 2^8 stays exact enough in fp16 hi/lo
+
+struct Bars {
+    uint64_t q_full;
+    uint64_t kv_full[NS], kv_empty[NS];
+    uint64_t bias_full[2], bias_empty[2];
+    uint64_t s_full[G], p_ready[G], pv_done[G];
+};
+
+PDK_DEV void tmem_st32(uint32_t addr, const uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+        ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+          "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]),
+          "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]),
+          "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31]) : "memory");
+}
+PDK_DEV void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+PDK_DEV void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate));
+}
+PDK_DEV float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+// fp32 -> packed (hi, lo) fp16 pair for two values in [0, 2^8]
+PDK_DEV void split2_pos(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    __half2 h = __floats2half2_rn(x0, x1);
+    float2 hf = __half22float2(h);
+    __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+    hi = *reinterpret_cast<uint32_t*>(&h);
+    lo = *reinterpret_cast<uint32_t*>(&l);
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+attention_umma_kernel(const __grid_constant__ CUtensorMap mQh, const __grid_constant__ CUtensorMap mQl,
+                      const __grid_constant__ CUtensorMap mKh, const __grid_constant__ CUtensorMap mKl,
+                      const __grid_constant__ CUtensorMap mVh, const __grid_constant__ CUtensorMap mVl,
+                      const __grid_constant__ CUtensorMap mBias, const AttnArgs p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) Bars bars;
+    __shared__ uint32_t tmem_slot;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b0 = blockIdx.x * G, qt = blockIdx.y, h = blockIdx.z;
+    const int ng = min(G, p.B - b0);
+    const int S = p.S_pad;
+    const int NJ = S / BKV;
+    const int U = NJ * ng;
+    const uint32_t sm = (smem_u32(smem_raw) + 1023u) & ~1023u;
+
+    if (threadIdx.x == 0) {
+        mbar_init(smem_u32(&bars.q_full), 1);
+        for (int s = 0; s < NS; ++s) { mbar_init(smem_u32(&bars.kv_full[s]), 1); mbar_init(smem_u32(&bars.kv_empty[s]), 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&bars.bias_full[b]), 1); mbar_init(smem_u32(&bars.bias_empty[b]), ng * 128); }
+        for (int g = 0; g < G; ++g) {
+            mbar_init(smem_u32(&bars.s_full[g]), 1);
+            mbar_init(smem_u32(&bars.p_ready[g]), 128);
+            mbar_init(smem_u32(&bars.pv_done[g]), 1);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 9) tmem_alloc(smem_u32(&tmem_slot), TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+
+    if (warp == 8) {
+        // ================================================================= TMA producer
+        if (lane == 0) {
+            tma_prefetch_desc(&mQh); tma_prefetch_desc(&mKh); tma_prefetch_desc(&mVh); tma_prefetch_desc(&mBias);
+            const uint32_t qbar = smem_u32(&bars.q_full);
+            mbar_expect_tx(qbar, ng * 2 * Q_PLANE);
+            for (int g = 0; g < ng; ++g) {
+                const int row = ((b0 + g) * p.H + h) * S + qt * BQ;
+                tma_load_2d(sm + OFF_Q + g * 2 * Q_PLANE, &mQh, qbar, 0, row);
+                tma_load_2d(sm + OFF_Q + g * 2 * Q_PLANE + Q_PLANE, &mQl, qbar, 0, row);
+            }
+            int i = 0;
+            for (int j = 0; j < NJ; ++j) {
+                const int bb = j & 1;
+                mbar_wait(smem_u32(&bars.bias_empty[bb]), (((uint32_t)j >> 1) & 1u) ^ 1u);
+                const uint32_t bbar = smem_u32(&bars.bias_full[bb]);
+                mbar_expect_tx(bbar, BIAS_TILE);
+                tma_load_2d(sm + OFF_BIAS + bb * BIAS_TILE, &mBias, bbar, j * BKV, h * S + qt * BQ);
+                tma_load_2d(sm + OFF_BIAS + bb * BIAS_TILE + BIAS_HALF, &mBias, bbar, j * BKV + 32, h * S + qt * BQ);
+                for (int g = 0; g < ng; ++g, ++i) {
+                    const int st = i % NS;
+                    mbar_wait(smem_u32(&bars.kv_empty[st]), (((uint32_t)(i / NS)) & 1u) ^ 1u);
+                    const uint32_t kbar = smem_u32(&bars.kv_full[st]);
+                    mbar_expect_tx(kbar, KV_STAGE);
+                    const int row = ((b0 + g) * p.H + h) * S + j * BKV;
+                    const uint32_t dst = sm + OFF_KV + st * KV_STAGE;
+                    tma_load_2d(dst, &mKh, kbar, 0, row);
+                    tma_load_2d(dst + KV_PLANE, &mKl, kbar, 0, row);
+                    tma_load_2d(dst + 2 * KV_PLANE, &mVh, kbar, 0, row);
+                    tma_load_2d(dst + 3 * KV_PLANE, &mVl, kbar, 0, row);
+                }
+            }
+        }
+    } else if (warp == 9) {
+        // ================================================================= MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc_qk = umma_idesc_f16(BQ, BKV);          // M128 N64, both K-major
+            constexpr uint32_t idesc_pv = umma_idesc_f16(BQ, D, true);      // M128 N32, B (= V) MN-major
+            auto issue_qk = [&](int i) {
+                const int g = i % ng, st = i % NS;
+                mbar_wait(smem_u32(&bars.kv_full[st]), ((uint32_t)(i / NS)) & 1u);
+                tc_fence_after();
+                const uint32_t q = sm + OFF_Q + g * 2 * Q_PLANE, k = sm + OFF_KV + st * KV_STAGE;
+                const uint64_t qh = smem_desc(q, 512, kLayoutSw64), ql = smem_desc(q + Q_PLANE, 512, kLayoutSw64);
+                const uint64_t kh = smem_desc(k, 512, kLayoutSw64), kl = smem_desc(k + KV_PLANE, 512, kLayoutSw64);
+                const uint32_t d = tmem + COL_S + g * BKV;
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks) {
+                    const uint64_t o = (uint64_t)(ks * 2);
+                    umma_f16(d, ql + o, kh + o, idesc_qk, ks != 0);
+                    umma_f16(d, qh + o, kl + o, idesc_qk, 1u);
+                    umma_f16(d, qh + o, kh + o, idesc_qk, 1u);
+                }
+                umma_commit(smem_u32(&bars.s_full[g]));
+            };
+            mbar_wait(smem_u32(&bars.q_full), 0);
+            for (int i = 0; i < min(ng, U); ++i) issue_qk(i);
+            for (int i = 0; i < U; ++i) {
+                const int g = i % ng, j = i / ng, st = i % NS;
+                mbar_wait(smem_u32(&bars.p_ready[g]), (uint32_t)j & 1u);
+                tc_fence_after();
+                const uint32_t v = sm + OFF_KV + st * KV_STAGE + 2 * KV_PLANE;
+                const uint64_t vh = smem_desc(v, 512, kLayoutSw64), vl = smem_desc(v + KV_PLANE, 512, kLayoutSw64);
+                const uint32_t pa = tmem + COL_S + g * BKV, d = tmem + COL_O + g * D;
+#pragma unroll
+                for (int ks = 0; ks < BKV / 16; ++ks) {
+                    const uint64_t o = (uint64_t)((ks * 16 * 64) >> 4);     // 16 key rows of 64 bytes
+                    umma_f16_ts(d, pa + 32 + ks * 8, vh + o, idesc_pv, (j | ks) != 0);   // P_lo V_hi
+                    umma_f16_ts(d, pa + ks * 8, vl + o, idesc_pv, 1u);                  // P_hi V_lo
+                    umma_f16_ts(d, pa + ks * 8, vh + o, idesc_pv, 1u);                  // P_hi V_hi
+                }
+                umma_commit(smem_u32(&bars.kv_empty[st]));
+                umma_commit(smem_u32(&bars.pv_done[g]));
+                if (i + ng < U) issue_qk(i + ng);
+            }
+        }
+    } else {
+        // ================================================================= softmax warpgroups
+        const int wg = warp >> 2;
+        const int row = (warp & 3) * 32 + lane;                 // query row inside the tile == TMEM lane
+        const uint32_t tl = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+        float m_run[2] = {0.f, 0.f}, l_run[2] = {0.f, 0.f};
+        const uint32_t bias_row = (uint32_t)row * 128u;
+        const uint32_t sw = (uint32_t)(row & 7);
+        for (int j = 0; j < NJ; ++j) {
+#pragma unroll
+            for (int gi = 0; gi < 2; ++gi) {
+                const int g = wg + 2 * gi;
+                if (g >= ng) continue;
+                mbar_wait(smem_u32(&bars.s_full[g]), (uint32_t)j & 1u);
+                tc_fence_after();
+                uint32_t r0[32], r1[32];
+                tmem_ld32(tl + COL_S + g * BKV, r0);
+                tmem_ld32(tl + COL_S + g * BKV + 32, r1);
+                mbar_wait(smem_u32(&bars.bias_full[j & 1]), ((uint32_t)j >> 1) & 1u);
+                tmem_ld_wait();
+                float s[64];
+                const uint32_t bt = sm + OFF_BIAS + (j & 1) * BIAS_TILE + bias_row;
+                float mx = -INFINITY;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const float4 b4 = lds128(bt + (((uint32_t)c ^ sw) << 4));
+                    s[4 * c] = __uint_as_float(r0[4 * c]) + b4.x;
+                    s[4 * c + 1] = __uint_as_float(r0[4 * c + 1]) + b4.y;
+                    s[4 * c + 2] = __uint_as_float(r0[4 * c + 2]) + b4.z;
+                    s[4 * c + 3] = __uint_as_float(r0[4 * c + 3]) + b4.w;
+                    mx = fmaxf(mx, fmaxf(fmaxf(s[4 * c], s[4 * c + 1]), fmaxf(s[4 * c + 2], s[4 * c + 3])));
+                }
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const float4 b4 = lds128(bt + BIAS_HALF + (((uint32_t)c ^ sw) << 4));
+                    s[32 + 4 * c] = __uint_as_float(r1[4 * c]) + b4.x;
+                    s[32 + 4 * c + 1] = __uint_as_float(r1[4 * c + 1]) + b4.y;
+                    s[32 + 4 * c + 2] = __uint_as_float(r1[4 * c + 2]) + b4.z;
+                    s[32 + 4 * c + 3] = __uint_as_float(r1[4 * c + 3]) + b4.w;
+                    mx = fmaxf(mx, fmaxf(fmaxf(s[32 + 4 * c], s[32 + 4 * c + 1]), fmaxf(s[32 + 4 * c + 2], s[32 + 4 * c + 3])));
+                }
+                mbar_arrive(smem_u32(&bars.bias_empty[j & 1]));
+                // ---- running max with lazy rescale of O (in TMEM)
+                if (j == 0) {
+                    m_run[gi] = mx;
+                } else {
+                    mbar_wait(smem_u32(&bars.pv_done[g]), (uint32_t)(j - 1) & 1u);     // O_g is stable
+                    const bool need = mx > m_run[gi] + kRescaleThreshold;
+                    if (__any_sync(0xffffffffu, need)) {
+                        tc_fence_after();
+                        const float c = need ? ex2(m_run[gi] - mx) : 1.0f;
+                        if (need) m_run[gi] = mx;
+                        l_run[gi] *= c;
+                        uint32_t o[32];
+                        tmem_ld32(tl + COL_O + g * D, o);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int k = 0; k < 32; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * c);
+                        tmem_st32(tl + COL_O + g * D, o);
+                    }
+                }
+                // ---- P = exp2(S - m), row sum, split to fp16 hi/lo, back to TMEM over S
+                const float mref = m_run[gi];
+                uint32_t hi[32], lo[32];
+                float sum = 0.f;
+#pragma unroll
+                for (int k = 0; k < 32; ++k) {
+                    const float p0 = ex2(s[2 * k] - mref), p1 = ex2(s[2 * k + 1] - mref);
+                    sum += p0 + p1;
+                    split2_pos(p0, p1, hi[k], lo[k]);
+                }
+                l_run[gi] += sum;
+                tmem_st32(tl + COL_S + g * BKV, hi);
+                tmem_st32(tl + COL_S + g * BKV + 32, lo);
+                tmem_st_wait();
+                tc_fence_before();
+                mbar_arrive(smem_u32(&bars.p_ready[g]));
+            }
+        }
+        // ---- epilogue: O / l -> split planes
+#pragma unroll
+        for (int gi = 0; gi < 2; ++gi) {
+            const int g = wg + 2 * gi;
+            if (g >= ng) continue;
+            mbar_wait(smem_u32(&bars.pv_done[g]), (uint32_t)(NJ - 1) & 1u);
+            tc_fence_after();
+            uint32_t o[32];
+            tmem_ld32(tl + COL_O + g * D, o);
+            tmem_ld_wait();
+            const float inv = 1.0f / l_run[gi];
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k)
+                split2(__uint_as_float(o[2 * k]) * inv, __uint_as_float(o[2 * k + 1]) * inv, hi[k], lo[k]);
+            const size_t off = ((size_t)(b0 + g) * S + (size_t)qt * BQ + row) * p.c + (size_t)h * D;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                reinterpret_cast<uint4*>(p.oh + off)[k] = make_uint4(hi[4 * k], hi[4 * k + 1], hi[4 * k + 2], hi[4 * k + 3]);
+                reinterpret_cast<uint4*>(p.ol + off)[k] = make_uint4(lo[4 * k], lo[4 * k + 1], lo[4 * k + 2], lo[4 * k + 3]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) tmem_dealloc(tmem, TMEM_COLS);
+}
+
+}  // namespace
+
+cudaError_t launch_attention(const AttnArgs& a, cudaStream_t st) {
+    if (a.S_pad <= 0 || a.S_pad % BQ || a.c != a.H * D || a.B <= 0) return cudaErrorInvalidValue;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(attention_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    const uint64_t rows = (uint64_t)a.B * a.H * a.S_pad;
+    CUtensorMap mQh, mQl, mKh, mKl, mVh, mVl, mBias;
+    cudaError_t e;
+    if ((e = get_tensor_map_f16(a.qh, rows, D, D, BQ, D, 64, &mQh)) != cudaSuccess) return e;
+    if ((e = get_tensor_map_f16(a.ql, rows, D, D, BQ, D, 64, &mQl)) != cudaSuccess) return e;
+    if ((e = get_tensor_map_f16(a.kh, rows, D, D, BKV, D, 64, &mKh)) != cudaSuccess) return e;
+    if ((e = get_tensor_map_f16(a.kl, rows, D, D, BKV, D, 64, &mKl)) != cudaSuccess) return e;
+    if ((e = get_tensor_map_f16(a.vh, rows, D, D, BKV, D, 64, &mVh)) != cudaSuccess) return e;
+    if ((e = get_tensor_map_f16(a.vl, rows, D, D, BKV, D, 64, &mVl)) != cudaSuccess) return e;
+    if ((e = get_tensor_map_f32(a.bias, (uint64_t)a.H * a.S_pad, a.S_pad, a.S_pad, BQ, 32, 128, &mBias)) != cudaSuccess) return e;
+    dim3 grid((a.B + G - 1) / G, a.S_pad / BQ, a.H);
+    attention_umma_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(mQh, mQl, mKh, mKl, mVh, mVl, mBias, a);
+    return cudaGetLastError();
+}
+
+}  // namespace pdk

@@ -144,6 +144,242 @@ __global__ void __launch_bounds__(128) probe_kernel(const __grid_constant__ CUte
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128));
 }
 
+
+// ---- test 4: TS-mode PV.  P (fp32 in global) -> split -> tcgen05.st to TMEM (packed halves), V MN-major via TMA.
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accum));
+}
+__device__ __forceinline__ void tmem_st32(uint32_t addr, const uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+        ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+          "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]),
+          "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]),
+          "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31]) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32p(uint32_t addr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(addr));
+}
+
+// grid 1, block 128.  P [128][128] fp32 row-major; V planes [128][32] fp16 via TMA (box 32 x 128, SWIZZLE_64B); D [128][32]
+__global__ void __launch_bounds__(128) probe_ts_kernel(const __grid_constant__ CUtensorMap mapVh, const __grid_constant__ CUtensorMap mapVl,
+                                                       const float* __restrict__ P, float* __restrict__ D) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bars[2];
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t bar_tma = smem_u32(&bars[0]), bar_mma = smem_u32(&bars[1]);
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(256));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    if (tid == 0) { mbar_init(bar_tma, 1); mbar_init(bar_mma, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_base_s;
+    if (tid == 0) {
+        mbar_expect_tx(bar_tma, 2 * 128 * 64);
+        tma_load_2d(smem_u32(smem), &mapVh, bar_tma, 0, 0);
+        tma_load_2d(smem_u32(smem) + 8192, &mapVl, bar_tma, 0, 0);
+    }
+    // every thread owns one row of P: split into packed fp16 hi / lo and store to TMEM columns [0,64) / [64,128)
+    const float* prow = P + (size_t)tid * 128;
+    for (int half = 0; half < 2; ++half) {      // 64 elements = 32 packed columns per tcgen05.st
+        uint32_t hi[32], lo[32];
+        for (int i = 0; i < 32; ++i) {
+            const float x0 = prow[half * 64 + 2 * i], x1 = prow[half * 64 + 2 * i + 1];
+            __half2 h = __floats2half2_rn(x0, x1);
+            float2 hf = __half22float2(h);
+            __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+            hi[i] = *reinterpret_cast<uint32_t*>(&h);
+            lo[i] = *reinterpret_cast<uint32_t*>(&l);
+        }
+        tmem_st32(tmem + ((uint32_t)(warp * 32) << 16) + half * 32, hi);
+        tmem_st32(tmem + ((uint32_t)(warp * 32) << 16) + 64 + half * 32, lo);
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    mbar_wait(bar_tma, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (tid == 0) {
+        const uint32_t idesc = (1u << 4) | (1u << 16) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // N=32, B MN-major
+        const uint32_t hi_bits = ((512u >> 4) & 0x3FFF) | (1u << 14) | (4u << 29);
+        const uint64_t dvh = ((uint64_t)hi_bits << 32) | (1ull << 16) | ((smem_u32(smem) >> 4) & 0x3FFF);
+        const uint64_t dvl = ((uint64_t)hi_bits << 32) | (1ull << 16) | (((smem_u32(smem) + 8192) >> 4) & 0x3FFF);
+        const uint32_t d_t = tmem + 128;
+        for (int k = 0; k < 8; ++k) {           // 16 kv rows per slice: A advances 8 columns, V advances 1024 bytes
+            const uint64_t o = (uint64_t)((k * 1024) >> 4);
+            umma_f16_ts(d_t, tmem + 64 + k * 8, dvh + o, idesc, k != 0);     // Pl * Vh
+            umma_f16_ts(d_t, tmem + k * 8, dvl + o, idesc, 1u);             // Ph * Vl
+            umma_f16_ts(d_t, tmem + k * 8, dvh + o, idesc, 1u);             // Ph * Vh
+        }
+        umma_commit(bar_mma);
+    }
+    mbar_wait(bar_mma, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t v[32];
+    tmem_ld32p(tmem + ((uint32_t)(warp * 32) << 16) + 128, v);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    for (int i = 0; i < 32; ++i) D[(size_t)tid * 32 + i] = __uint_as_float(v[i]);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256));
+}
+
+// ---- test 5: per-SM rate micro-benchmarks (cycles via clock64); grid = 148 CTAs so every SM is busy.
+//   mode 0: tcgen05.ld x32 by 4 warps   mode 1: tcgen05.st x32 by 4 warps
+//   mode 2: SS MMA M128 N128 K16        mode 3: SS MMA M128 N32 K16 (B MN-major)   mode 4: TS MMA M128 N32 K16
+//   mode 5: SS MMA M128 N64 K16
+__global__ void __launch_bounds__(128) probe_rate_kernel(int mode, int iters, long long* out) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bars[1];
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const uint32_t bar = smem_u32(&bars[0]);
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    if (tid == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    for (int i = tid; i < 32768 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;   // fp16 1.0
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_base_s;
+    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+    long long t0 = clock64();
+    if (mode == 0) {
+        uint32_t acc = 0;
+        for (int it = 0; it < iters; ++it) {
+            uint32_t v[32];
+            tmem_ld32p(lane_base + (it & 7) * 32, v);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            acc += v[0] + v[31];
+        }
+        if (acc == 0x12345678u) out[1000] = acc;
+    } else if (mode == 1) {
+        uint32_t v[32];
+        for (int i = 0; i < 32; ++i) v[i] = tid + i;
+        for (int it = 0; it < iters; ++it) tmem_st32(lane_base + (it & 7) * 32, v);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    } else {
+        if (tid == 0) {
+            // modes >= 6: interleave independent accumulators / other shapes
+            //  6: SS N128, 2 accumulators   7: TS N32, 4 accumulators   8: SS N256   9: SS N32 (MN), 4 accumulators
+            // 10: SS N128 accumulate=0     11: TS N32, 8 accumulators  12: SS N128 + TS N32 alternating (attention mix)
+            int N = 128; bool mn = false, ts = false; int nacc = 1, dstride = 0; uint32_t accf = 1u;
+            switch (mode) {
+                case 2: N = 128; break;
+                case 3: N = 32; mn = true; break;
+                case 4: N = 32; mn = true; ts = true; break;
+                case 5: N = 64; break;
+                case 6: N = 128; nacc = 2; dstride = 128; break;
+                case 7: N = 32; mn = true; ts = true; nacc = 4; dstride = 32; break;
+                case 8: N = 256; break;
+                case 9: N = 32; mn = true; nacc = 4; dstride = 32; break;
+                case 10: N = 128; accf = 0u; break;
+                case 11: N = 32; mn = true; ts = true; nacc = 8; dstride = 32; break;
+                default: break;
+            }
+            const uint32_t hi_bits = ((512u >> 4) & 0x3FFF) | (1u << 14) | (4u << 29);
+            const uint64_t da = ((uint64_t)hi_bits << 32) | (1ull << 16) | ((smem_u32(smem) >> 4) & 0x3FFF);
+            const uint64_t db = ((uint64_t)hi_bits << 32) | (1ull << 16) | (((smem_u32(smem) + 16384) >> 4) & 0x3FFF);
+            if (mode == 12) {
+                const uint32_t id128 = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+                const uint32_t id32 = (1u << 4) | (1u << 16) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+                for (int it = 0; it < iters; it += 2) {
+                    umma_f16(tmem + 256 + ((it >> 1) & 1) * 128, da, db, id128, 1u);
+                    umma_f16_ts(tmem + 128 + ((it >> 1) & 3) * 32, tmem + (it & 7) * 8, db, id32, 1u);
+                }
+            } else {
+                const uint32_t idesc = (1u << 4) | (mn ? (1u << 16) : 0u) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+                for (int it = 0; it < iters; ++it) {
+                    const uint32_t d = tmem + 256 + (uint32_t)((it % nacc) * dstride);
+                    if (ts) umma_f16_ts(d, tmem + (it & 7) * 8, db, idesc, accf);
+                    else    umma_f16(d, da, db, idesc, accf);
+                }
+            }
+            umma_commit(bar);
+        }
+        mbar_wait(bar, 0);
+    }
+    long long t1 = clock64();
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) out[blockIdx.x] = t1 - t0;
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+}
+
+
+// ---- test 6: MMA issue-rate benchmark with compile-time shapes, 8 MMAs unrolled per iteration (like a real k-loop)
+template <int N, bool TS, bool MN, int NACC>
+__global__ void __launch_bounds__(128) probe_rate2_kernel(int iters, long long* out) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bars[1];
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const uint32_t bar = smem_u32(&bars[0]);
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    if (tid == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    for (int i = tid; i < 49152 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_base_s;
+    long long t0 = clock64();
+    if (tid == 0) {
+        constexpr uint32_t idesc = (1u << 4) | (MN ? (1u << 16) : 0u) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t hi_bits = ((512u >> 4) & 0x3FFF) | (1u << 14) | (4u << 29);
+        const uint64_t da = ((uint64_t)hi_bits << 32) | (1ull << 16) | ((smem_u32(smem) >> 4) & 0x3FFF);
+        const uint64_t db = ((uint64_t)hi_bits << 32) | (1ull << 16) | (((smem_u32(smem) + 16384) >> 4) & 0x3FFF);
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const uint32_t d = tmem + 256 + (uint32_t)((u % NACC) * (N <= 64 ? 32 : 128));
+                if constexpr (TS) umma_f16_ts(d, tmem + u * 8, db + (uint64_t)(u & 1) * 2, idesc, 1u);
+                else              umma_f16(d, da + (uint64_t)(u & 1) * 2, db + (uint64_t)(u & 1) * 2, idesc, 1u);
+            }
+        }
+        umma_commit(bar);
+    }
+    mbar_wait(bar, 0);
+    long long t1 = clock64();
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) out[blockIdx.x] = t1 - t0;
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+}
+
+template <int N, bool TS, bool MN, int NACC>
+static void run_rate2(const char* name, long long* dout) {
+    CK(cudaFuncSetAttribute(probe_rate2_kernel<N, TS, MN, NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 49152 + 1024));
+    const int iters = 500;
+    probe_rate2_kernel<N, TS, MN, NACC><<<148, 128, 49152 + 1024>>>(iters, dout);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    std::vector<long long> h(148);
+    CK(cudaMemcpy(h.data(), dout, 148 * 8, cudaMemcpyDeviceToHost));
+    double avg = 0; for (auto v : h) avg += (double)v; avg /= 148.0;
+    printf("RATE2 %-40s cycles/MMA=%.1f  (floor %d)\n", name, avg / (iters * 8.0), 128 * N / 256);
+}
+
 typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                              const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -178,6 +414,77 @@ int main(int argc, char** argv) {
     const int test = argc > 1 ? atoi(argv[1]) : 0;
     const int variant = argc > 2 ? atoi(argv[2]) : 0;
     EncodeFn enc = get_encode();
+
+    if (test == 4) {
+        std::vector<float> Pm(128 * 128), Vm(128 * 32);
+        srand(77);
+        for (auto& v : Pm) v = (rand() % 10001) / 10000.0f * (rand() % 7 == 0 ? 1.0f : 0.01f);
+        for (auto& v : Vm) v = (rand() % 2001 - 1000) / 500.0f;
+        std::vector<__half> Vh(Vm.size()), Vl(Vm.size());
+        for (size_t i = 0; i < Vm.size(); ++i) { Vh[i] = __float2half_rn(Vm[i]); Vl[i] = __float2half_rn(Vm[i] - __half2float(Vh[i])); }
+        float *dP, *dD; __half *dVh, *dVl;
+        CK(cudaMalloc(&dP, Pm.size() * 4)); CK(cudaMalloc(&dD, 128 * 32 * 4)); CK(cudaMalloc(&dVh, Vm.size() * 2)); CK(cudaMalloc(&dVl, Vm.size() * 2));
+        CK(cudaMemcpy(dP, Pm.data(), Pm.size() * 4, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(dVh, Vh.data(), Vm.size() * 2, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(dVl, Vl.data(), Vm.size() * 2, cudaMemcpyHostToDevice));
+        CUtensorMap mVh = make_map(enc, dVh, 128, 32, 128, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+        CUtensorMap mVl = make_map(enc, dVl, 128, 32, 128, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+        CK(cudaFuncSetAttribute(probe_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 + 1024));
+        probe_ts_kernel<<<1, 128, 16384 + 1024>>>(mVh, mVl, dP, dD);
+        CK(cudaGetLastError());
+        CK(cudaDeviceSynchronize());
+        std::vector<float> Dm(128 * 32);
+        CK(cudaMemcpy(Dm.data(), dD, Dm.size() * 4, cudaMemcpyDeviceToHost));
+        double max_err = 0, max_ref = 0;
+        for (int i = 0; i < 128; ++i)
+            for (int j = 0; j < 32; ++j) {
+                double ref = 0;
+                for (int k = 0; k < 128; ++k) ref += (double)Pm[i * 128 + k] * (double)Vm[k * 32 + j];
+                max_err = fmax(max_err, fabs(ref - (double)Dm[i * 32 + j]));
+                max_ref = fmax(max_ref, fabs(ref));
+            }
+        const bool pass = max_err <= 2e-5 * max_ref + 1e-6;
+        printf("PROBE test=4 (TS-mode PV, P via tcgen05.st) max_err=%.3e max_ref=%.3f %s\n", max_err, max_ref, pass ? "PASS" : "FAIL");
+        return pass ? 0 : 1;
+    }
+
+    if (test == 6) {
+        long long* dout; CK(cudaMalloc(&dout, 2048 * 8));
+        run_rate2<128, false, false, 1>("SS N128 1 acc", dout);
+        run_rate2<128, false, false, 2>("SS N128 2 acc", dout);
+        run_rate2<64, false, false, 1>("SS N64 1 acc", dout);
+        run_rate2<64, false, false, 4>("SS N64 4 acc", dout);
+        run_rate2<32, false, true, 1>("SS N32 (B MN) 1 acc", dout);
+        run_rate2<32, false, true, 4>("SS N32 (B MN) 4 acc", dout);
+        run_rate2<32, true, true, 1>("TS N32 (B MN) 1 acc", dout);
+        run_rate2<32, true, true, 4>("TS N32 (B MN) 4 acc", dout);
+        run_rate2<256, false, false, 1>("SS N256 1 acc", dout);
+        run_rate2<128, true, false, 1>("TS N128 1 acc", dout);
+        return 0;
+    }
+    if (test == 5) {
+        long long* dout; CK(cudaMalloc(&dout, 2048 * 8));
+        CK(cudaFuncSetAttribute(probe_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 + 1024));
+        const int iters = 2000;
+        const char* names[] = {"tcgen05.ld 32x32b.x32 (4 warps)", "tcgen05.st 32x32b.x32 (4 warps)", "SS MMA M128 N128 K16",
+                               "SS MMA M128 N32 K16 (B MN)", "TS MMA M128 N32 K16 (B MN)", "SS MMA M128 N64 K16",
+                               "SS N128, 2 accumulators", "TS N32, 4 accumulators", "SS N256", "SS N32 MN, 4 accumulators",
+                               "SS N128 accumulate=0", "TS N32, 8 accumulators", "SS N128 + TS N32 alternating (per pair)"};
+        for (int mode = 0; mode < 13; ++mode) {
+            probe_rate_kernel<<<148, 128, 32768 + 1024>>>(mode, iters, dout);
+            CK(cudaGetLastError());
+            CK(cudaDeviceSynchronize());
+            std::vector<long long> h(148);
+            CK(cudaMemcpy(h.data(), dout, 148 * 8, cudaMemcpyDeviceToHost));
+            double avg = 0; for (auto v : h) avg += (double)v; avg /= 148.0;
+            const double per = avg / iters;
+            double bytes = mode < 2 ? 4.0 * 4096.0 : 0.0;      // 4 warps x 4 KB per iteration
+            printf("RATE mode=%d %-34s cycles/iter=%.1f", mode, names[mode], per);
+            if (mode < 2) printf("  => %.1f B/clk/SM", bytes / per);
+            printf("\n");
+        }
+        return 0;
+    }
     const int M = 128;
     int N = 128, K = 256, kb_elems = 64;
     if (test == 2) { N = 32; K = 128; }
