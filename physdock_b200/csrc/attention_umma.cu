@@ -117,7 +117,7 @@ attention_umma_kernel(const __grid_constant__ CUtensorMap mQh, const __grid_cons
 
     if (warp == 8) {
         // ================================================================= TMA producer
-        if (lane == 0) {
+        if (elect_one()) {
             tma_prefetch_desc(&mQh); tma_prefetch_desc(&mKh); tma_prefetch_desc(&mVh); tma_prefetch_desc(&mBias);
             const uint32_t qbar = smem_u32(&bars.q_full);
             mbar_expect_tx(qbar, ng * 2 * Q_PLANE);
@@ -126,17 +126,23 @@ attention_umma_kernel(const __grid_constant__ CUtensorMap mQh, const __grid_cons
                 tma_load_2d(sm + OFF_Q + g * 2 * Q_PLANE, &mQh, qbar, 0, row);
                 tma_load_2d(sm + OFF_Q + g * 2 * Q_PLANE + Q_PLANE, &mQl, qbar, 0, row);
             }
-            int i = 0;
-            for (int j = 0; j < NJ; ++j) {
-                const int bb = j & 1;
-                mbar_wait(smem_u32(&bars.bias_empty[bb]), (((uint32_t)j >> 1) & 1u) ^ 1u);
+        }
+        __syncwarp();
+        int i = 0;
+        for (int j = 0; j < NJ; ++j) {
+            const int bb = j & 1;
+            mbar_wait(smem_u32(&bars.bias_empty[bb]), (((uint32_t)j >> 1) & 1u) ^ 1u);
+            if (elect_one()) {
                 const uint32_t bbar = smem_u32(&bars.bias_full[bb]);
                 mbar_expect_tx(bbar, BIAS_TILE);
                 tma_load_2d(sm + OFF_BIAS + bb * BIAS_TILE, &mBias, bbar, j * BKV, h * S + qt * BQ);
                 tma_load_2d(sm + OFF_BIAS + bb * BIAS_TILE + BIAS_HALF, &mBias, bbar, j * BKV + 32, h * S + qt * BQ);
-                for (int g = 0; g < ng; ++g, ++i) {
-                    const int st = i % NS;
-                    mbar_wait(smem_u32(&bars.kv_empty[st]), (((uint32_t)(i / NS)) & 1u) ^ 1u);
+            }
+            __syncwarp();
+            for (int g = 0; g < ng; ++g, ++i) {
+                const int st = i % NS;
+                mbar_wait(smem_u32(&bars.kv_empty[st]), (((uint32_t)(i / NS)) & 1u) ^ 1u);
+                if (elect_one()) {
                     const uint32_t kbar = smem_u32(&bars.kv_full[st]);
                     mbar_expect_tx(kbar, KV_STAGE);
                     const int row = ((b0 + g) * p.H + h) * S + j * BKV;
@@ -146,17 +152,18 @@ attention_umma_kernel(const __grid_constant__ CUtensorMap mQh, const __grid_cons
                     tma_load_2d(dst + 2 * KV_PLANE, &mVh, kbar, 0, row);
                     tma_load_2d(dst + 3 * KV_PLANE, &mVl, kbar, 0, row);
                 }
+                __syncwarp();
             }
         }
     } else if (warp == 9) {
-        // ================================================================= MMA issuer
-        if (lane == 0) {
-            constexpr uint32_t idesc_qk = umma_idesc_f16(BQ, BKV);          // M128 N64, both K-major
-            constexpr uint32_t idesc_pv = umma_idesc_f16(BQ, D, true);      // M128 N32, B (= V) MN-major
-            auto issue_qk = [&](int i) {
-                const int g = i % ng, st = i % NS;
-                mbar_wait(smem_u32(&bars.kv_full[st]), ((uint32_t)(i / NS)) & 1u);
-                tc_fence_after();
+        // ================================================================= MMA issuer (whole warp loops, one lane issues)
+        constexpr uint32_t idesc_qk = umma_idesc_f16(BQ, BKV);          // M128 N64, both K-major
+        constexpr uint32_t idesc_pv = umma_idesc_f16(BQ, D, true);      // M128 N32, B (= V) MN-major
+        auto issue_qk = [&](int i) {
+            const int g = i % ng, st = i % NS;
+            mbar_wait(smem_u32(&bars.kv_full[st]), ((uint32_t)(i / NS)) & 1u);
+            tc_fence_after();
+            if (elect_one()) {
                 const uint32_t q = sm + OFF_Q + g * 2 * Q_PLANE, k = sm + OFF_KV + st * KV_STAGE;
                 const uint64_t qh = smem_desc(q, 512, kLayoutSw64), ql = smem_desc(q + Q_PLANE, 512, kLayoutSw64);
                 const uint64_t kh = smem_desc(k, 512, kLayoutSw64), kl = smem_desc(k + KV_PLANE, 512, kLayoutSw64);
@@ -169,13 +176,16 @@ attention_umma_kernel(const __grid_constant__ CUtensorMap mQh, const __grid_cons
                     umma_f16(d, qh + o, kh + o, idesc_qk, 1u);
                 }
                 umma_commit(smem_u32(&bars.s_full[g]));
-            };
-            mbar_wait(smem_u32(&bars.q_full), 0);
-            for (int i = 0; i < min(ng, U); ++i) issue_qk(i);
-            for (int i = 0; i < U; ++i) {
-                const int g = i % ng, j = i / ng, st = i % NS;
-                mbar_wait(smem_u32(&bars.p_ready[g]), (uint32_t)j & 1u);
-                tc_fence_after();
+            }
+            __syncwarp();
+        };
+        mbar_wait(smem_u32(&bars.q_full), 0);
+        for (int i = 0; i < min(ng, U); ++i) issue_qk(i);
+        for (int i = 0; i < U; ++i) {
+            const int g = i % ng, j = i / ng, st = i % NS;
+            mbar_wait(smem_u32(&bars.p_ready[g]), (uint32_t)j & 1u);
+            tc_fence_after();
+            if (elect_one()) {
                 const uint32_t v = sm + OFF_KV + st * KV_STAGE + 2 * KV_PLANE;
                 const uint64_t vh = smem_desc(v, 512, kLayoutSw64), vl = smem_desc(v + KV_PLANE, 512, kLayoutSw64);
                 const uint32_t pa = tmem + COL_S + g * BKV, d = tmem + COL_O + g * D;
@@ -188,8 +198,9 @@ attention_umma_kernel(const __grid_constant__ CUtensorMap mQh, const __grid_cons
                 }
                 umma_commit(smem_u32(&bars.kv_empty[st]));
                 umma_commit(smem_u32(&bars.pv_done[g]));
-                if (i + ng < U) issue_qk(i + ng);
             }
+            __syncwarp();
+            if (i + ng < U) issue_qk(i + ng);
         }
     } else {
         // ================================================================= softmax warpgroups

@@ -65,11 +65,11 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant_
     const uint32_t tmem = tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
-            for (int kt = 0; kt < KT; ++kt) {
-                const int s = kt % STAGES;
-                const uint32_t ph = (uint32_t)(kt / STAGES) & 1u;
-                mbar_wait(empty(s), ph ^ 1u);
+        for (int kt = 0; kt < KT; ++kt) {
+            const int s = kt % STAGES;
+            const uint32_t ph = (uint32_t)(kt / STAGES) & 1u;
+            mbar_wait(empty(s), ph ^ 1u);
+            if (elect_one()) {
                 mbar_expect_tx(full(s), STAGE_BYTES);
                 const uint32_t dst = ring + s * STAGE_BYTES;
                 tma_load_2d(dst, &mAh, full(s), kt * BK, m0);
@@ -77,15 +77,16 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant_
                 tma_load_2d(dst + 2 * TILE_BYTES, &mWh, full(s), kt * BK, n0);
                 tma_load_2d(dst + 3 * TILE_BYTES, &mWl, full(s), kt * BK, n0);
             }
+            __syncwarp();
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_f16(BM, BN);
-            for (int kt = 0; kt < KT; ++kt) {
-                const int s = kt % STAGES;
-                const uint32_t ph = (uint32_t)(kt / STAGES) & 1u;
-                mbar_wait(full(s), ph);
-                tc_fence_after();
+        constexpr uint32_t idesc = umma_idesc_f16(BM, BN);
+        for (int kt = 0; kt < KT; ++kt) {
+            const int s = kt % STAGES;
+            const uint32_t ph = (uint32_t)(kt / STAGES) & 1u;
+            mbar_wait(full(s), ph);
+            tc_fence_after();
+            if (elect_one()) {
                 const uint32_t src = ring + s * STAGE_BYTES;
                 const uint64_t ah = smem_desc(src, 512, kLayoutSw64), al = smem_desc(src + TILE_BYTES, 512, kLayoutSw64);
                 const uint64_t wh = smem_desc(src + 2 * TILE_BYTES, 512, kLayoutSw64);
@@ -98,8 +99,9 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant_
                     umma_f16(tmem, ah + o, wh + o, idesc, 1u);
                 }
                 umma_commit(empty(s));      // frees the smem stage once these MMAs have read it
+                if (kt == KT - 1) umma_commit(tfull);   // accumulator complete
             }
-            umma_commit(tfull);             // accumulator complete
+            __syncwarp();
         }
     } else {
         // ---------------------------------------------------------------- epilogue (128 threads = 128 rows)

@@ -11,6 +11,20 @@
 
 namespace pdk {
 
+// One lane of a fully converged warp (elect.sync).  Issue code for TMA / tcgen05 must sit under this predicate
+// in warp-uniform control flow: under a divergent `if (lane == 0)` the compiler cannot prove uniformity of the
+// uniform-register operands and wraps every UTCHMMA / UTMALDG in an ELECT + BRA.U.ANY waterfall loop
+// (~100 cycles per issued MMA, measured: profiles/r01_attention_v2a_ncu.txt).
+PDK_DEV bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // ------------------------------------------------------------------------------------- mbarrier
 PDK_DEV void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
