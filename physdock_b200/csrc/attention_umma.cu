@@ -11,15 +11,17 @@
 //   warp 8  TMA producer   : Q planes of the group (once); per key tile the bias tile [128 x 64] fp32 (two
 //                            SWIZZLE_128B boxes, double buffered) and per unit K_hi,K_lo,V_hi,V_lo [64 x 32] fp16
 //                            (SWIZZLE_64B, 6-stage ring)
-//   warp 9  MMA issuer     : S_g = Q_g K^T   (SS, M128 N64 K16 x 2 slices x 3 split products) into TMEM buffer g
-//                            O_g += P_g V    (TS: P from TMEM, V MN-major from smem; 4 slices x 3 products)
+//   warp 9  QK issuer      : S_g = Q_g K^T   (SS, M128 N64 K16 x 2 slices x 3 split products) into TMEM buffer g
+//   warp 10 PV issuer      : O_g += P_g V    (TS: P from TMEM, V MN-major from smem; 4 slices x 3 products)
+//                            Two issuing warps because one warp's serialized waits/commits left the tensor pipe
+//                            idle ~40% of the time (profiles/r01_attention_timeline.txt); QK(j,g) is ordered after
+//                            PV(j-1,g) through the pv_done barrier (S and P share a TMEM buffer).
 //   warps 0-3 / 4-7        : two softmax warpgroups (samples g even / odd).  Thread = one query row: reads its 64
 //                            scores with tcgen05.ld, adds the bias row, row max / exp2 / row sum entirely in
 //                            registers (no shuffles), splits P into fp16 hi/lo and writes it back over S with
 //                            tcgen05.st (S and P alias).  O is rescaled lazily (only when the row max grows by
 //                            more than 2^8), directly in TMEM.
-// TMEM: 4 x 64 columns S/P + 4 x 32 columns O.  MMAs of one thread execute in issue order, which is what makes
-// the S/P aliasing and the accumulator reuse safe without extra barriers.
+// TMEM: 4 x 64 columns S/P + 4 x 64 columns O (P_hi V_hi + P_lo V_hi | P_hi V_lo, summed in the epilogue).
 #include "common.cuh"
 #include "kernels.h"
 #include "umma.cuh"
@@ -40,10 +42,13 @@ constexpr int OFF_Q = 0;
 constexpr int OFF_BIAS = G * 2 * Q_PLANE;            // 64 KB
 constexpr int OFF_KV = OFF_BIAS + 2 * BIAS_TILE;     // 128 KB
 constexpr int SMEM_BYTES = OFF_KV + NS * KV_STAGE + 1024;   // 225 KB
-constexpr int NTHREADS = 320;
+constexpr int NTHREADS = 352;
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t COL_S = 0, COL_O = 256;
 constexpr float kRescaleThreshold = 8.0f;            // log2 domain: P <= 2^8 stays exact enough in fp16 hi/lo
+
+// debug timeline: slot layout trace[(unit * 8 + k)]
+#define TRACE(unit, k) do { if (p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0) p.trace[(unit) * 8 + (k)] = clock64(); } while (0)
 
 struct Bars {
     uint64_t q_full;
@@ -73,13 +78,32 @@ PDK_DEV float4 lds128(uint32_t addr) {
     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
     return v;
 }
-// fp32 -> packed (hi, lo) fp16 pair for two values in [0, 2^8]
-PDK_DEV void split2_pos(float x0, float x1, uint32_t& hi, uint32_t& lo) {
-    __half2 h = __floats2half2_rn(x0, x1);
-    float2 hf = __half22float2(h);
-    __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
-    hi = *reinterpret_cast<uint32_t*>(&h);
-    lo = *reinterpret_cast<uint32_t*>(&l);
+// ---- packed fp32x2 arithmetic (FADD2 / FMNMX3 on sm_100): halves the issue slots of the softmax inner loops
+PDK_DEV uint64_t pack2(float a, float b) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+PDK_DEV void unpack2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+PDK_DEV uint64_t add2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+PDK_DEV float max3(float a, float b, float c) {
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+// p0, p1 in [0, 2^8] -> packed fp16 (hi, lo) planes.  hi = p truncated to 11 significant bits (cvt.rz), whose fp32
+// value is p & 0xffffe000 (exact for p >= 2^-14; below that the mismatch is < 2^-25 absolute); lo = fp16(p - hi).
+PDK_DEV void split2_pos(float p0, float p1, uint32_t& hi, uint32_t& lo) {
+    asm("cvt.rz.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(p1), "f"(p0));
+    const float n0 = __uint_as_float((__float_as_uint(p0) & 0xffffe000u) ^ 0x80000000u);
+    const float n1 = __uint_as_float((__float_as_uint(p1) & 0xffffe000u) ^ 0x80000000u);
+    float l0, l1;
+    unpack2(add2(pack2(p0, p1), pack2(n0, n1)), l0, l1);
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(l1), "f"(l0));
 }
 
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -95,7 +119,6 @@ attention_umma_kernel(const __grid_constant__ CUtensorMap mQh, const __grid_cons
     const int ng = min(G, p.B - b0);
     const int S = p.S_pad;
     const int NJ = S / BKV;
-    const int U = NJ * ng;
     const uint32_t sm = (smem_u32(smem_raw) + 1023u) & ~1023u;
 
     if (threadIdx.x == 0) {
@@ -128,7 +151,8 @@ attention_umma_kernel(const __grid_constant__ CUtensorMap mQh, const __grid_cons
             }
         }
         __syncwarp();
-        int i = 0;
+        int st = 0;
+        uint32_t kv_par = 0;
         for (int j = 0; j < NJ; ++j) {
             const int bb = j & 1;
             mbar_wait(smem_u32(&bars.bias_empty[bb]), (((uint32_t)j >> 1) & 1u) ^ 1u);
@@ -139,9 +163,8 @@ attention_umma_kernel(const __grid_constant__ CUtensorMap mQh, const __grid_cons
                 tma_load_2d(sm + OFF_BIAS + bb * BIAS_TILE + BIAS_HALF, &mBias, bbar, j * BKV + 32, h * S + qt * BQ);
             }
             __syncwarp();
-            for (int g = 0; g < ng; ++g, ++i) {
-                const int st = i % NS;
-                mbar_wait(smem_u32(&bars.kv_empty[st]), (((uint32_t)(i / NS)) & 1u) ^ 1u);
+            for (int g = 0; g < ng; ++g) {
+                mbar_wait(smem_u32(&bars.kv_empty[st]), kv_par ^ 1u);
                 if (elect_one()) {
                     const uint32_t kbar = smem_u32(&bars.kv_full[st]);
                     mbar_expect_tx(kbar, KV_STAGE);
@@ -153,54 +176,74 @@ attention_umma_kernel(const __grid_constant__ CUtensorMap mQh, const __grid_cons
                     tma_load_2d(dst + 3 * KV_PLANE, &mVl, kbar, 0, row);
                 }
                 __syncwarp();
+                if (++st == NS) { st = 0; kv_par ^= 1u; }
             }
         }
     } else if (warp == 9) {
-        // ================================================================= MMA issuer (whole warp loops, one lane issues)
+        // ================================================================= QK issuer (whole warp loops, one lane issues)
+        // S_g(j) = Q_g K_g(j)^T.  The S buffer of sample g doubles as its P buffer, so QK(j,g) waits for PV(j-1,g).
         constexpr uint32_t idesc_qk = umma_idesc_f16(BQ, BKV);          // M128 N64, both K-major
-        constexpr uint32_t idesc_pv = umma_idesc_f16(BQ, D, true);      // M128 N32, B (= V) MN-major
-        auto issue_qk = [&](int i) {
-            const int g = i % ng, st = i % NS;
-            mbar_wait(smem_u32(&bars.kv_full[st]), ((uint32_t)(i / NS)) & 1u);
-            tc_fence_after();
-            if (elect_one()) {
-                const uint32_t q = sm + OFF_Q + g * 2 * Q_PLANE, k = sm + OFF_KV + st * KV_STAGE;
-                const uint64_t qh = smem_desc(q, 512, kLayoutSw64), ql = smem_desc(q + Q_PLANE, 512, kLayoutSw64);
-                const uint64_t kh = smem_desc(k, 512, kLayoutSw64), kl = smem_desc(k + KV_PLANE, 512, kLayoutSw64);
-                const uint32_t d = tmem + COL_S + g * BKV;
-#pragma unroll
-                for (int ks = 0; ks < 2; ++ks) {
-                    const uint64_t o = (uint64_t)(ks * 2);
-                    umma_f16(d, ql + o, kh + o, idesc_qk, ks != 0);
-                    umma_f16(d, qh + o, kl + o, idesc_qk, 1u);
-                    umma_f16(d, qh + o, kh + o, idesc_qk, 1u);
-                }
-                umma_commit(smem_u32(&bars.s_full[g]));
-            }
-            __syncwarp();
-        };
         mbar_wait(smem_u32(&bars.q_full), 0);
-        for (int i = 0; i < min(ng, U); ++i) issue_qk(i);
-        for (int i = 0; i < U; ++i) {
-            const int g = i % ng, j = i / ng, st = i % NS;
-            mbar_wait(smem_u32(&bars.p_ready[g]), (uint32_t)j & 1u);
-            tc_fence_after();
-            if (elect_one()) {
-                const uint32_t v = sm + OFF_KV + st * KV_STAGE + 2 * KV_PLANE;
-                const uint64_t vh = smem_desc(v, 512, kLayoutSw64), vl = smem_desc(v + KV_PLANE, 512, kLayoutSw64);
-                const uint32_t pa = tmem + COL_S + g * BKV, d = tmem + COL_O + g * D;
+        int g = 0, st = 0;
+        uint32_t kv_par = 0;
+        for (int j = 0; j < NJ; ++j) {
+            for (g = 0; g < ng; ++g) {
+                mbar_wait(smem_u32(&bars.kv_full[st]), kv_par);
+                if (j > 0) mbar_wait(smem_u32(&bars.pv_done[g]), (uint32_t)(j - 1) & 1u);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t q = sm + OFF_Q + g * 2 * Q_PLANE, k = sm + OFF_KV + st * KV_STAGE;
+                    const uint64_t qh = smem_desc(q, 512, kLayoutSw64), ql = smem_desc(q + Q_PLANE, 512, kLayoutSw64);
+                    const uint64_t kh = smem_desc(k, 512, kLayoutSw64), kl = smem_desc(k + KV_PLANE, 512, kLayoutSw64);
+                    const uint32_t d = tmem + COL_S + g * BKV;
 #pragma unroll
-                for (int ks = 0; ks < BKV / 16; ++ks) {
-                    const uint64_t o = (uint64_t)((ks * 16 * 64) >> 4);     // 16 key rows of 64 bytes
-                    umma_f16_ts(d, pa + 32 + ks * 8, vh + o, idesc_pv, (j | ks) != 0);   // P_lo V_hi
-                    umma_f16_ts(d, pa + ks * 8, vl + o, idesc_pv, 1u);                  // P_hi V_lo
-                    umma_f16_ts(d, pa + ks * 8, vh + o, idesc_pv, 1u);                  // P_hi V_hi
+                    for (int ks = 0; ks < 2; ++ks) {
+                        const uint64_t o = (uint64_t)(ks * 2);
+                        umma_f16(d, ql + o, kh + o, idesc_qk, ks != 0);
+                        umma_f16(d, qh + o, kl + o, idesc_qk, 1u);
+                        umma_f16(d, qh + o, kh + o, idesc_qk, 1u);
+                    }
+                    umma_commit(smem_u32(&bars.s_full[g]));
                 }
-                umma_commit(smem_u32(&bars.kv_empty[st]));
-                umma_commit(smem_u32(&bars.pv_done[g]));
+                __syncwarp();
+                TRACE(j * ng + g, 2);                          // QK issued
+                if (++st == NS) { st = 0; kv_par ^= 1u; }
             }
-            __syncwarp();
-            if (i + ng < U) issue_qk(i + ng);
+        }
+    } else if (warp == 10) {
+        // ================================================================= PV issuer
+        // O_g += P_g(j) V_g(j): P from TMEM (written by the softmax threads over S), V MN-major from smem.
+        // The V_hi and V_lo tiles sit back to back in the stage, so one MN-major descriptor with LBO = tile size
+        // presents [V_hi | V_lo] as a single N = 64 operand: P_hi [V_hi|V_lo] is one MMA (O columns 0-31 and 32-63),
+        // P_lo V_hi a second one onto columns 0-31.  2 MMAs per slice instead of 3 (every M128 MMA costs >= 45 cycles).
+        constexpr uint32_t idesc_pv = umma_idesc_f16(BQ, D, true);      // M128 N32, B (= V) MN-major
+        constexpr uint32_t idesc_pv2 = umma_idesc_f16(BQ, 2 * D, true); // M128 N64
+        int g = 0, st = 0;
+        uint32_t kv_par = 0;
+        for (int j = 0; j < NJ; ++j) {
+            for (g = 0; g < ng; ++g) {
+                mbar_wait(smem_u32(&bars.kv_full[st]), kv_par);        // visibility of the V tile to this warp
+                mbar_wait(smem_u32(&bars.p_ready[g]), (uint32_t)j & 1u);
+                TRACE(j * ng + g, 0);                          // PV warp saw p_ready
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t v = sm + OFF_KV + st * KV_STAGE + 2 * KV_PLANE;
+                    const uint64_t vh = smem_desc(v, 512, kLayoutSw64);
+                    const uint64_t vcat = smem_desc_lbo(v, KV_PLANE, 512, kLayoutSw64);
+                    const uint32_t pa = tmem + COL_S + g * BKV, d = tmem + COL_O + g * 2 * D;
+#pragma unroll
+                    for (int ks = 0; ks < BKV / 16; ++ks) {
+                        const uint64_t o = (uint64_t)((ks * 16 * 64) >> 4);     // 16 key rows of 64 bytes
+                        umma_f16_ts(d, pa + ks * 8, vcat + o, idesc_pv2, (j | ks) != 0);    // P_hi [V_hi | V_lo]
+                        umma_f16_ts(d, pa + 32 + ks * 8, vh + o, idesc_pv, 1u);             // P_lo V_hi
+                    }
+                    umma_commit(smem_u32(&bars.kv_empty[st]));
+                    umma_commit(smem_u32(&bars.pv_done[g]));
+                }
+                __syncwarp();
+                TRACE(j * ng + g, 1);                          // PV issued
+                if (++st == NS) { st = 0; kv_par ^= 1u; }
+            }
         }
     } else {
         // ================================================================= softmax warpgroups
@@ -215,35 +258,42 @@ attention_umma_kernel(const __grid_constant__ CUtensorMap mQh, const __grid_cons
             for (int gi = 0; gi < 2; ++gi) {
                 const int g = wg + 2 * gi;
                 if (g >= ng) continue;
+                if ((warp & 3) == 0) TRACE(j * ng + g, 3);     // softmax starts waiting for S
                 mbar_wait(smem_u32(&bars.s_full[g]), (uint32_t)j & 1u);
+                if ((warp & 3) == 0) TRACE(j * ng + g, 4);     // S arrived
                 tc_fence_after();
                 uint32_t r0[32], r1[32];
                 tmem_ld32(tl + COL_S + g * BKV, r0);
                 tmem_ld32(tl + COL_S + g * BKV + 32, r1);
                 mbar_wait(smem_u32(&bars.bias_full[j & 1]), ((uint32_t)j >> 1) & 1u);
                 tmem_ld_wait();
-                float s[64];
+                uint64_t s2[32];                         // the 64 scores of this row as 32 fp32x2 pairs
                 const uint32_t bt = sm + OFF_BIAS + (j & 1) * BIAS_TILE + bias_row;
                 float mx = -INFINITY;
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                     const float4 b4 = lds128(bt + (((uint32_t)c ^ sw) << 4));
-                    s[4 * c] = __uint_as_float(r0[4 * c]) + b4.x;
-                    s[4 * c + 1] = __uint_as_float(r0[4 * c + 1]) + b4.y;
-                    s[4 * c + 2] = __uint_as_float(r0[4 * c + 2]) + b4.z;
-                    s[4 * c + 3] = __uint_as_float(r0[4 * c + 3]) + b4.w;
-                    mx = fmaxf(mx, fmaxf(fmaxf(s[4 * c], s[4 * c + 1]), fmaxf(s[4 * c + 2], s[4 * c + 3])));
+                    s2[2 * c] = add2(pack2(__uint_as_float(r0[4 * c]), __uint_as_float(r0[4 * c + 1])), pack2(b4.x, b4.y));
+                    s2[2 * c + 1] = add2(pack2(__uint_as_float(r0[4 * c + 2]), __uint_as_float(r0[4 * c + 3])), pack2(b4.z, b4.w));
+                    float a0, a1, a2, a3;
+                    unpack2(s2[2 * c], a0, a1);
+                    unpack2(s2[2 * c + 1], a2, a3);
+                    mx = max3(mx, a0, a1);
+                    mx = max3(mx, a2, a3);
                 }
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                     const float4 b4 = lds128(bt + BIAS_HALF + (((uint32_t)c ^ sw) << 4));
-                    s[32 + 4 * c] = __uint_as_float(r1[4 * c]) + b4.x;
-                    s[32 + 4 * c + 1] = __uint_as_float(r1[4 * c + 1]) + b4.y;
-                    s[32 + 4 * c + 2] = __uint_as_float(r1[4 * c + 2]) + b4.z;
-                    s[32 + 4 * c + 3] = __uint_as_float(r1[4 * c + 3]) + b4.w;
-                    mx = fmaxf(mx, fmaxf(fmaxf(s[32 + 4 * c], s[32 + 4 * c + 1]), fmaxf(s[32 + 4 * c + 2], s[32 + 4 * c + 3])));
+                    s2[16 + 2 * c] = add2(pack2(__uint_as_float(r1[4 * c]), __uint_as_float(r1[4 * c + 1])), pack2(b4.x, b4.y));
+                    s2[16 + 2 * c + 1] = add2(pack2(__uint_as_float(r1[4 * c + 2]), __uint_as_float(r1[4 * c + 3])), pack2(b4.z, b4.w));
+                    float a0, a1, a2, a3;
+                    unpack2(s2[16 + 2 * c], a0, a1);
+                    unpack2(s2[16 + 2 * c + 1], a2, a3);
+                    mx = max3(mx, a0, a1);
+                    mx = max3(mx, a2, a3);
                 }
                 mbar_arrive(smem_u32(&bars.bias_empty[j & 1]));
+                if ((warp & 3) == 0) TRACE(j * ng + g, 5);     // S + bias in registers, row max known
                 // ---- running max with lazy rescale of O (in TMEM)
                 if (j == 0) {
                     m_run[gi] = mx;
@@ -255,30 +305,42 @@ attention_umma_kernel(const __grid_constant__ CUtensorMap mQh, const __grid_cons
                         const float c = need ? ex2(m_run[gi] - mx) : 1.0f;
                         if (need) m_run[gi] = mx;
                         l_run[gi] *= c;
-                        uint32_t o[32];
-                        tmem_ld32(tl + COL_O + g * D, o);
+                        uint32_t o[32], o2[32];
+                        tmem_ld32(tl + COL_O + g * 2 * D, o);
+                        tmem_ld32(tl + COL_O + g * 2 * D + 32, o2);
                         tmem_ld_wait();
 #pragma unroll
-                        for (int k = 0; k < 32; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * c);
-                        tmem_st32(tl + COL_O + g * D, o);
+                        for (int k = 0; k < 32; ++k) {
+                            o[k] = __float_as_uint(__uint_as_float(o[k]) * c);
+                            o2[k] = __float_as_uint(__uint_as_float(o2[k]) * c);
+                        }
+                        tmem_st32(tl + COL_O + g * 2 * D, o);
+                        tmem_st32(tl + COL_O + g * 2 * D + 32, o2);
                     }
                 }
                 // ---- P = exp2(S - m), row sum, split to fp16 hi/lo, back to TMEM over S
                 const float mref = m_run[gi];
+                const uint64_t negm = pack2(-mref, -mref);
                 uint32_t hi[32], lo[32];
-                float sum = 0.f;
+                uint64_t sum2 = pack2(0.f, 0.f);
 #pragma unroll
                 for (int k = 0; k < 32; ++k) {
-                    const float p0 = ex2(s[2 * k] - mref), p1 = ex2(s[2 * k + 1] - mref);
-                    sum += p0 + p1;
+                    float x0, x1;
+                    unpack2(add2(s2[k], negm), x0, x1);
+                    const float p0 = ex2(x0), p1 = ex2(x1);
+                    sum2 = add2(sum2, pack2(p0, p1));
                     split2_pos(p0, p1, hi[k], lo[k]);
                 }
+                float sum, sum_b;
+                unpack2(sum2, sum, sum_b);
+                sum += sum_b;
                 l_run[gi] += sum;
                 tmem_st32(tl + COL_S + g * BKV, hi);
                 tmem_st32(tl + COL_S + g * BKV + 32, lo);
                 tmem_st_wait();
                 tc_fence_before();
                 mbar_arrive(smem_u32(&bars.p_ready[g]));
+                if ((warp & 3) == 0) TRACE(j * ng + g, 6);     // P published
             }
         }
         // ---- epilogue: O / l -> split planes
@@ -288,14 +350,16 @@ attention_umma_kernel(const __grid_constant__ CUtensorMap mQh, const __grid_cons
             if (g >= ng) continue;
             mbar_wait(smem_u32(&bars.pv_done[g]), (uint32_t)(NJ - 1) & 1u);
             tc_fence_after();
-            uint32_t o[32];
-            tmem_ld32(tl + COL_O + g * D, o);
+            uint32_t o[32], o2[32];
+            tmem_ld32(tl + COL_O + g * 2 * D, o);
+            tmem_ld32(tl + COL_O + g * 2 * D + 32, o2);
             tmem_ld_wait();
             const float inv = 1.0f / l_run[gi];
             uint32_t hi[16], lo[16];
 #pragma unroll
             for (int k = 0; k < 16; ++k)
-                split2(__uint_as_float(o[2 * k]) * inv, __uint_as_float(o[2 * k + 1]) * inv, hi[k], lo[k]);
+                split2((__uint_as_float(o[2 * k]) + __uint_as_float(o2[2 * k])) * inv,
+                       (__uint_as_float(o[2 * k + 1]) + __uint_as_float(o2[2 * k + 1])) * inv, hi[k], lo[k]);
             const size_t off = ((size_t)(b0 + g) * S + (size_t)qt * BQ + row) * p.c + (size_t)h * D;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -311,7 +375,12 @@ attention_umma_kernel(const __grid_constant__ CUtensorMap mQh, const __grid_cons
 
 }  // namespace
 
-cudaError_t launch_attention(const AttnArgs& a, cudaStream_t st) {
+static long long* g_trace = nullptr;
+void set_attention_trace(long long* buf) { g_trace = buf; }
+
+cudaError_t launch_attention(const AttnArgs& a_in, cudaStream_t st) {
+    AttnArgs a = a_in;
+    a.trace = g_trace;
     if (a.S_pad <= 0 || a.S_pad % BQ || a.c != a.H * D || a.B <= 0) return cudaErrorInvalidValue;
     static bool configured = false;
     if (!configured) {

@@ -110,7 +110,7 @@ int run_block(const pdk_dit& h, const pdk_block_weights& bw, const Workspace& ws
     g.norm_q = bw.norm_q; g.norm_k = bw.norm_k; g.c = c; g.rows_per_sample = (int)Sp;
     g.rms_eps = eps; g.q_scale = kLog2e / sqrtf((float)kHeadDim);
     PDK_TRY("gemm(qkv)", launch_gemm(EPI_QKV, g, st));
-    AttnArgs at{ws.qh, ws.ql, ws.kh, ws.kl, ws.vh, ws.vl, bias, ws.oh, ws.ol, (int)B, Hh, (int)Sp, c};
+    AttnArgs at{ws.qh, ws.ql, ws.kh, ws.kl, ws.vh, ws.vl, bias, ws.oh, ws.ol, (int)B, Hh, (int)Sp, c, nullptr};
     PDK_TRY("attention", launch_attention(at, st));
     g = GemmArgs{};
     g.Ah = ws.oh; g.Al = ws.ol; g.lda = c;
@@ -142,6 +142,8 @@ int run_block(const pdk_dit& h, const pdk_block_weights& bw, const Workspace& ws
 extern "C" {
 
 int pdk_abi_version(void) { return PDK_ABI_VERSION; }
+// debug hook (not part of the public header): per-unit timeline of the attention kernel, see tools/trace_attention.py
+void pdk_debug_attention_trace(void* buf) { set_attention_trace(reinterpret_cast<long long*>(buf)); }
 const char* pdk_last_error(void) { return g_err.c_str(); }
 int64_t pdk_pad_len(int64_t n) { return pad128(n); }
 
@@ -390,7 +392,7 @@ int pdk_op_gemm_qkv(const void* Ah, const void* Al, int64_t lda, const void* Wh,
 }
 int pdk_op_attention(const void* qh, const void* ql, const void* kh, const void* kl, const void* vh, const void* vl,
                      const float* bias, void* oh, void* ol, int64_t B, int64_t Hh, int64_t S_pad, void* stream) {
-    AttnArgs a{H(qh), H(ql), H(kh), H(kl), H(vh), H(vl), bias, H(oh), H(ol), (int)B, (int)Hh, (int)S_pad, (int)(Hh * kHeadDim)};
+    AttnArgs a{H(qh), H(ql), H(kh), H(kl), H(vh), H(vl), bias, H(oh), H(ol), (int)B, (int)Hh, (int)S_pad, (int)(Hh * kHeadDim), nullptr};
     PDK_TRY("attention", launch_attention(a, S(stream)));
     return 0;
 }

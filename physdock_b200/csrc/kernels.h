@@ -42,8 +42,10 @@ struct AttnArgs {
     const float* bias;
     __half* oh; __half* ol;
     int B, H, S_pad, c;
+    long long* trace;   // debug only: per-unit clock64 stamps of CTA (0,0,0); nullptr in production
 };
 cudaError_t launch_attention(const AttnArgs& a, cudaStream_t st);
+void set_attention_trace(long long* buf);   // debug hook used by tools/trace_attention.py
 
 // ----------------------------------------------------------------------------- pair-bias prepass
 // bias[l][h][i][j] = log2e * ( sum_c wfold[l*H+h][c] * xhat(pair[i][j])[c] + bfold[l*H+h] + (mask==0 ? -inf_ : 0) )

@@ -106,6 +106,12 @@ PDK_DEV uint64_t smem_desc(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t layo
     return ((uint64_t)(((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | (layout << 29)) << 32) | (1ull << 16) |
            (uint64_t)((smem_addr >> 4) & 0x3FFF);
 }
+// Same with an explicit leading-dimension byte offset: for MN-major operands LBO is the distance between
+// consecutive swizzle atoms along MN (validated: tests/cuda/umma_probe.cu test 4 variant 1).
+PDK_DEV uint64_t smem_desc_lbo(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+    return ((uint64_t)(((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | (layout << 29)) << 32) |
+           ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | (uint64_t)((smem_addr >> 4) & 0x3FFF);
+}
 // Instruction descriptor for kind::f16 (cute::UMMA::InstrDescriptor): c_format F32 [4,6)=1, a/b format F16=0,
 // a_major bit 15, b_major bit 16 (0 = K-major, 1 = MN-major), N>>3 [17,23), M>>4 [24,29).
 __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N, bool b_mn_major = false) {

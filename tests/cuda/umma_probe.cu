@@ -173,7 +173,7 @@ __device__ __forceinline__ void tmem_ld32p(uint32_t addr, uint32_t (&v)[32]) {
 
 // grid 1, block 128.  P [128][128] fp32 row-major; V planes [128][32] fp16 via TMA (box 32 x 128, SWIZZLE_64B); D [128][32]
 __global__ void __launch_bounds__(128) probe_ts_kernel(const __grid_constant__ CUtensorMap mapVh, const __grid_constant__ CUtensorMap mapVl,
-                                                       const float* __restrict__ P, float* __restrict__ D) {
+                                                       const float* __restrict__ P, float* __restrict__ D, int concat, uint32_t lbo_bytes) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t bars[2];
     __shared__ uint32_t tmem_base_s;
@@ -219,20 +219,32 @@ __global__ void __launch_bounds__(128) probe_ts_kernel(const __grid_constant__ C
         const uint64_t dvh = ((uint64_t)hi_bits << 32) | (1ull << 16) | ((smem_u32(smem) >> 4) & 0x3FFF);
         const uint64_t dvl = ((uint64_t)hi_bits << 32) | (1ull << 16) | (((smem_u32(smem) + 8192) >> 4) & 0x3FFF);
         const uint32_t d_t = tmem + 128;
-        for (int k = 0; k < 8; ++k) {           // 16 kv rows per slice: A advances 8 columns, V advances 1024 bytes
-            const uint64_t o = (uint64_t)((k * 1024) >> 4);
-            umma_f16_ts(d_t, tmem + 64 + k * 8, dvh + o, idesc, k != 0);     // Pl * Vh
-            umma_f16_ts(d_t, tmem + k * 8, dvl + o, idesc, 1u);             // Ph * Vl
-            umma_f16_ts(d_t, tmem + k * 8, dvh + o, idesc, 1u);             // Ph * Vh
+        if (!concat) {
+            for (int k = 0; k < 8; ++k) {           // 16 kv rows per slice: A advances 8 columns, V advances 1024 bytes
+                const uint64_t o = (uint64_t)((k * 1024) >> 4);
+                umma_f16_ts(d_t, tmem + 64 + k * 8, dvh + o, idesc, k != 0);     // Pl * Vh
+                umma_f16_ts(d_t, tmem + k * 8, dvl + o, idesc, 1u);             // Ph * Vl
+                umma_f16_ts(d_t, tmem + k * 8, dvh + o, idesc, 1u);             // Ph * Vh
+            }
+        } else {
+            // [Vh | Vl] as one MN-major B operand of N = 64: second 32-column atom at LBO bytes (the Vl tile)
+            const uint32_t idesc64 = (1u << 4) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const uint64_t dcat = ((uint64_t)hi_bits << 32) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((smem_u32(smem) >> 4) & 0x3FFF);
+            for (int k = 0; k < 8; ++k) {
+                const uint64_t o = (uint64_t)((k * 1024) >> 4);
+                umma_f16_ts(d_t, tmem + k * 8, dcat + o, idesc64, k != 0);      // Ph * [Vh | Vl]  -> D[:, 0:64]
+                umma_f16_ts(d_t, tmem + 64 + k * 8, dvh + o, idesc, 1u);        // Pl * Vh         -> D[:, 0:32]
+            }
         }
         umma_commit(bar_mma);
     }
     mbar_wait(bar_mma, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    uint32_t v[32];
+    uint32_t v[32], v2[32];
     tmem_ld32p(tmem + ((uint32_t)(warp * 32) << 16) + 128, v);
+    tmem_ld32p(tmem + ((uint32_t)(warp * 32) << 16) + 160, v2);
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    for (int i = 0; i < 32; ++i) D[(size_t)tid * 32 + i] = __uint_as_float(v[i]);
+    for (int i = 0; i < 32; ++i) D[(size_t)tid * 32 + i] = __uint_as_float(v[i]) + (concat ? __uint_as_float(v2[i]) : 0.f);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256));
@@ -430,7 +442,7 @@ int main(int argc, char** argv) {
         CUtensorMap mVh = make_map(enc, dVh, 128, 32, 128, 32, CU_TENSOR_MAP_SWIZZLE_64B);
         CUtensorMap mVl = make_map(enc, dVl, 128, 32, 128, 32, CU_TENSOR_MAP_SWIZZLE_64B);
         CK(cudaFuncSetAttribute(probe_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 + 1024));
-        probe_ts_kernel<<<1, 128, 16384 + 1024>>>(mVh, mVl, dP, dD);
+        probe_ts_kernel<<<1, 128, 16384 + 1024>>>(mVh, mVl, dP, dD, variant > 0 ? 1 : 0, variant == 2 ? 512u : (variant == 3 ? 64u : 8192u));
         CK(cudaGetLastError());
         CK(cudaDeviceSynchronize());
         std::vector<float> Dm(128 * 32);
@@ -444,7 +456,7 @@ int main(int argc, char** argv) {
                 max_ref = fmax(max_ref, fabs(ref));
             }
         const bool pass = max_err <= 2e-5 * max_ref + 1e-6;
-        printf("PROBE test=4 (TS-mode PV, P via tcgen05.st) max_err=%.3e max_ref=%.3f %s\n", max_err, max_ref, pass ? "PASS" : "FAIL");
+        printf("PROBE test=4 variant=%d (TS-mode PV, P via tcgen05.st; variant>0: [Vh|Vl] N=64 concat) max_err=%.3e max_ref=%.3f %s\n", max_err, max_ref, pass ? "PASS" : "FAIL");
         return pass ? 0 : 1;
     }
 
