@@ -9,9 +9,9 @@
 //
 // PERSISTENT kernel: one CTA per SM walks 128x128 output tiles (n fastest, so consecutive CTAs share the A tile
 // in L2); 320 threads, warp-specialised:
-//   warp 0   : TMA producer: 4 plane tiles [128 rows x 32 halves] per stage, SWIZZLE_64B, 6-stage ring (192 KB)
+//   warp 0   : TMA producer: 4 plane tiles [128 rows x 64 halves] per stage, SWIZZLE_128B, 3-stage ring (192 KB)
 //              that runs ahead across tile boundaries
-//   warp 1   : TMEM allocator + MMA issuer: 6 x tcgen05.mma.kind::f16 M128 N128 K16 per stage into one of TWO
+//   warp 1   : TMEM allocator + MMA issuer: 12 x tcgen05.mma.kind::f16 M128 N128 K16 per stage into one of TWO
 //              128-column accumulators, so the epilogue of tile i overlaps the main loop of tile i+1
 //   warps 2-9: epilogue (two warps per TMEM lane quarter, two 32-column chunks each).  A THREAD owns one output
 //              row and reads 32 consecutive accumulator columns per tcgen05.ld -- exactly one attention head / one
@@ -26,8 +26,10 @@ namespace pdk {
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 32, STAGES = 6, ACC = 2;
-constexpr int TILE_BYTES = 128 * BK * 2;            // 8 KB: one fp16 plane tile, 64-byte rows
+// BK = 64 halves = 128-byte rows: TMA boxes narrower than 128 B run at less than half rate (28 vs 65 B/clk/SM,
+// tests/cuda/umma_probe.cu test 7), which made the BK = 32 version L2-fabric bound.
+constexpr int BM = 128, BN = 128, BK = 64, STAGES = 3, ACC = 2;
+constexpr int TILE_BYTES = 128 * BK * 2;            // 16 KB: one fp16 plane tile, 128-byte rows (SWIZZLE_128B)
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;         // A_hi, A_lo, W_hi, W_lo
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;   // + slack to 1024-align the ring
 constexpr int NTHREADS = 320;
@@ -114,9 +116,9 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant_
                 tc_fence_after();
                 if (elect_one()) {
                     const uint32_t src = ring + s * STAGE_BYTES;
-                    const uint64_t ah = smem_desc(src, 512, kLayoutSw64), al = smem_desc(src + TILE_BYTES, 512, kLayoutSw64);
-                    const uint64_t wh = smem_desc(src + 2 * TILE_BYTES, 512, kLayoutSw64);
-                    const uint64_t wl = smem_desc(src + 3 * TILE_BYTES, 512, kLayoutSw64);
+                    const uint64_t ah = smem_desc(src, 1024, kLayoutSw128), al = smem_desc(src + TILE_BYTES, 1024, kLayoutSw128);
+                    const uint64_t wh = smem_desc(src + 2 * TILE_BYTES, 1024, kLayoutSw128);
+                    const uint64_t wl = smem_desc(src + 3 * TILE_BYTES, 1024, kLayoutSw128);
 #pragma unroll
                     for (int ks = 0; ks < BK / 16; ++ks) {
                         const uint64_t o = (uint64_t)(ks * 2);                  // +32 bytes (>>4) per K=16 slice
@@ -235,10 +237,10 @@ cudaError_t launch_one(const GemmArgs& a, cudaStream_t st) {
     }
     CUtensorMap mAh, mAl, mWh, mWl;
     cudaError_t e;
-    if ((e = get_tensor_map_f16(a.Ah, a.M, a.K, a.lda, BM, BK, 64, &mAh)) != cudaSuccess) return e;
-    if ((e = get_tensor_map_f16(a.Al, a.M, a.K, a.lda, BM, BK, 64, &mAl)) != cudaSuccess) return e;
-    if ((e = get_tensor_map_f16(a.Wh, a.N, a.K, a.ldw, BN, BK, 64, &mWh)) != cudaSuccess) return e;
-    if ((e = get_tensor_map_f16(a.Wl, a.N, a.K, a.ldw, BN, BK, 64, &mWl)) != cudaSuccess) return e;
+    if ((e = get_tensor_map_f16(a.Ah, a.M, a.K, a.lda, BM, BK, 128, &mAh)) != cudaSuccess) return e;
+    if ((e = get_tensor_map_f16(a.Al, a.M, a.K, a.lda, BM, BK, 128, &mAl)) != cudaSuccess) return e;
+    if ((e = get_tensor_map_f16(a.Wh, a.N, a.K, a.ldw, BN, BK, 128, &mWh)) != cudaSuccess) return e;
+    if ((e = get_tensor_map_f16(a.Wl, a.N, a.K, a.ldw, BN, BK, 128, &mWl)) != cudaSuccess) return e;
     static int num_sms = 0;
     if (num_sms == 0) {
         int dev = 0;

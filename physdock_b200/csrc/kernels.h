@@ -8,7 +8,7 @@ namespace pdk {
 
 // ----------------------------------------------------------------------------- split-fp16 GEMM
 // C[M,N] = A[M,K] * W[N,K]^T with A, W given as (hi, lo) fp16 planes; fp32 accumulation of
-// Ah*Wh + Ah*Wl + Al*Wh.  M % 128 == 0, N % 128 == 0, K % 32 == 0 (activations are padded to S_pad).
+// Ah*Wh + Ah*Wl + Al*Wh.  M % 128 == 0, N % 128 == 0, K % 64 == 0 (activations are padded to S_pad).
 enum GemmEpilogue {
     EPI_STORE = 0,       // out[M,N] (fp32) = act(acc + bias)
     EPI_GATE_RESID = 1,  // out[M,N] (fp32, in place) += (acc + bias) * gate[sample(row)][col]

@@ -418,6 +418,133 @@ static CUtensorMap make_map(EncodeFn enc, void* ptr, uint64_t rows, uint64_t col
     return m;
 }
 
+
+// ---- test 7: TMA streaming rate per SM.  Each CTA streams `iters` stages of NLOADS x [128 rows x 64 B] tiles through a
+// DEPTH-deep ring (no consumer work: a stage is recycled as soon as it lands).  mode 0: all CTAs read the same rows
+// (L2-resident), mode 1: every CTA reads its own rows of a large tensor (HBM stream).
+template <int DEPTH, int NLOADS>
+__global__ void __launch_bounds__(64) probe_tma_kernel(const __grid_constant__ CUtensorMap map, int iters, int mode, int rows_total,
+                                                       long long* out) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bars[DEPTH];
+    const int tid = threadIdx.x;
+    if (tid == 0) { for (int i = 0; i < DEPTH; ++i) mbar_init(smem_u32(&bars[i]), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    __syncthreads();
+    long long t0 = clock64();
+    if (tid == 0) {
+        const uint32_t sb = (smem_u32(smem) + 1023u) & ~1023u;
+        int row_base = mode == 0 ? 0 : (int)(((long long)blockIdx.x * 8191) % (rows_total / 128 - NLOADS)) * 128;
+        for (int it = 0; it < iters + DEPTH; ++it) {
+            const int s = it % DEPTH;
+            if (it >= DEPTH) mbar_wait(smem_u32(&bars[s]), ((it / DEPTH) - 1) & 1);
+            if (it < iters) {
+                mbar_expect_tx(smem_u32(&bars[s]), NLOADS * 8192);
+                for (int l = 0; l < NLOADS; ++l) {
+                    int row = row_base + l * 128;
+                    if (mode == 1) { row_base = (row_base + 128 * NLOADS * 37) % (rows_total - 128 * NLOADS); row = row_base + l * 128; }
+                    tma_load_2d(sb + s * (NLOADS * 8192) + l * 8192, &map, smem_u32(&bars[s]), 0, row);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    long long t1 = clock64();
+    if (tid == 0) out[blockIdx.x] = t1 - t0;
+}
+
+template <int DEPTH, int NLOADS>
+static void run_tma(EncodeFn enc, __half* buf, int rows_total, int mode, long long* dout, bool wide = false) {
+    // wide: view the same memory as [rows/2][64 halves] and fetch [64 rows x 128 B] boxes (also 8 KB each)
+    CUtensorMap m = wide ? make_map(enc, buf, rows_total / 2, 64, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B)
+                         : make_map(enc, buf, rows_total, 32, 128, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (wide) { printf("[128B-wide boxes] "); rows_total /= 2; }
+    const int smem = DEPTH * NLOADS * 8192 + 1024;
+    CK(cudaFuncSetAttribute(probe_tma_kernel<DEPTH, NLOADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int iters = 400;
+    probe_tma_kernel<DEPTH, NLOADS><<<148, 64, smem>>>(m, iters, mode, rows_total, dout);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    std::vector<long long> h(148);
+    CK(cudaMemcpy(h.data(), dout, 148 * 8, cudaMemcpyDeviceToHost));
+    double avg = 0; for (auto v : h) avg += (double)v; avg /= 148.0;
+    printf("TMA depth=%d loads/stage=%d (%d KB/stage) mode=%s: %.1f B/clk/SM  (%.0f cycles/stage)\n", DEPTH, NLOADS, NLOADS * 8,
+           mode ? "HBM-distinct" : "L2-shared", (double)iters * NLOADS * 8192 / avg, avg / iters);
+}
+
+
+// ---- test 8: TMA multicast within a cluster.  Each CTA of a cluster of size C loads 1/C of every stage and multicasts it to
+// all C CTAs; a stage is recycled when ALL CTAs have seen it land (remote mbarrier arrives), as a real GEMM ring would.
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t local_bar, uint32_t cta) {
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_bar), "r"(cta));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
+}
+template <int C, int DEPTH>
+__global__ void __launch_bounds__(64) probe_mc_kernel(const __grid_constant__ CUtensorMap map, int iters, int rows_total, long long* out) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t full[DEPTH], empty[DEPTH];
+    const int tid = threadIdx.x;
+    const uint32_t rank = cluster_rank();
+    if (tid == 0) {
+        for (int i = 0; i < DEPTH; ++i) { mbar_init(smem_u32(&full[i]), 1); mbar_init(smem_u32(&empty[i]), C); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    long long t0 = clock64();
+    if (tid == 0) {
+        const uint32_t sb = (smem_u32(smem) + 1023u) & ~1023u;
+        constexpr int STAGE = 32768, SLICE = STAGE / C;           // each CTA loads SLICE bytes = SLICE/64 rows
+        int row_base = (int)((((long long)(blockIdx.x / C)) * 8191) % (rows_total / 512 - 1)) * 512;
+        for (int it = 0; it < iters + DEPTH; ++it) {
+            const int s = it % DEPTH;
+            if (it >= DEPTH) {           // consume: wait for the stage issued DEPTH iterations ago, then release it everywhere
+                mbar_wait(smem_u32(&full[s]), ((it / DEPTH) - 1) & 1);
+                for (uint32_t c = 0; c < (uint32_t)C; ++c) mbar_arrive_remote(smem_u32(&empty[s]), c);
+            }
+            if (it < iters) {
+                if (it >= DEPTH) mbar_wait(smem_u32(&empty[s]), ((it / DEPTH) - 1) & 1);
+                mbar_expect_tx(smem_u32(&full[s]), STAGE);
+                row_base = (row_base + 512 * 37) % (rows_total - 512);
+                // rows [row_base + rank*SLICE/64, +SLICE/64) of this stage; box = 128 rows x 64 B = 8 KB
+                for (int l = 0; l < SLICE / 8192; ++l) {
+                    const int piece = rank * (SLICE / 8192) + l;
+                    tma_load_2d_mc(sb + s * STAGE + piece * 8192, &map, smem_u32(&full[s]), 0, row_base + piece * 128, (uint16_t)((1u << C) - 1));
+                }
+            }
+        }
+    }
+    __syncthreads();
+    long long t1 = clock64();
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (tid == 0) out[blockIdx.x] = t1 - t0;
+}
+template <int C, int DEPTH>
+static void run_mc(EncodeFn enc, __half* buf, int rows_total, long long* dout) {
+    CUtensorMap m = make_map(enc, buf, rows_total, 32, 128, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+    const int smem = DEPTH * 32768 + 1024;
+    CK(cudaFuncSetAttribute(probe_mc_kernel<C, DEPTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int iters = 400;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(148 / C * C); cfg.blockDim = dim3(64); cfg.dynamicSmemBytes = smem; cfg.stream = 0;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    CK(cudaLaunchKernelEx(&cfg, probe_mc_kernel<C, DEPTH>, m, iters, rows_total, dout));
+    CK(cudaDeviceSynchronize());
+    const int n = 148 / C * C;
+    std::vector<long long> h(n);
+    CK(cudaMemcpy(h.data(), dout, n * 8, cudaMemcpyDeviceToHost));
+    double avg = 0; for (auto v : h) avg += (double)v; avg /= n;
+    printf("MULTICAST cluster=%d depth=%d: delivered %.1f B/clk/SM (L2 reads %.1f B/clk/SM), %.0f cycles/stage\n", C, DEPTH,
+           (double)iters * 32768 / avg, (double)iters * 32768 / C / avg, avg / iters);
+}
+
 static uint32_t desc_hi(uint32_t sbo_bytes, uint32_t layout_type) {
     return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | (layout_type << 29);   // SBO | version=1 (bit 46) | layout (bits 61..63)
 }
@@ -460,6 +587,34 @@ int main(int argc, char** argv) {
         return pass ? 0 : 1;
     }
 
+
+
+    if (test == 8) {
+        long long* dout; CK(cudaMalloc(&dout, 2048 * 8));
+        const int rows_total = 1 << 23;
+        __half* buf; CK(cudaMalloc(&buf, (size_t)rows_total * 64));
+        CK(cudaMemset(buf, 0, (size_t)rows_total * 64));
+        run_mc<1, 6>(enc, buf, rows_total, dout);
+        run_mc<2, 6>(enc, buf, rows_total, dout);
+        run_mc<4, 6>(enc, buf, rows_total, dout);
+        return 0;
+    }
+    if (test == 7) {
+        long long* dout; CK(cudaMalloc(&dout, 2048 * 8));
+        const int rows_total = 1 << 23;            // 8M rows x 64 B = 512 MB
+        __half* buf; CK(cudaMalloc(&buf, (size_t)rows_total * 64));
+        CK(cudaMemset(buf, 0, (size_t)rows_total * 64));
+        for (int mode = 0; mode < 2; ++mode) {
+            run_tma<3, 4>(enc, buf, rows_total, mode, dout);
+            run_tma<6, 4>(enc, buf, rows_total, mode, dout);
+            run_tma<12, 2>(enc, buf, rows_total, mode, dout);
+            run_tma<24, 1>(enc, buf, rows_total, mode, dout);
+            run_tma<6, 4>(enc, buf, rows_total, mode, dout, true);
+            run_tma<12, 4>(enc, buf, rows_total, mode, dout, true);
+            run_tma<6, 4>(enc, buf, 1 << 18, mode, dout);        // 16 MB working set: L2-resident, distinct per CTA
+        }
+        return 0;
+    }
     if (test == 6) {
         long long* dout; CK(cudaMalloc(&dout, 2048 * 8));
         run_rate2<128, false, false, 1>("SS N128 1 acc", dout);

@@ -33,7 +33,7 @@ def pad_rows(x, S_pad):
 
 
 # ------------------------------------------------------------------------------------- GEMM / attention core
-@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (256, 384, 128), (384, 128, 1408), (128, 512, 512)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 384, 128), (384, 128, 1408), (128, 512, 512), (2048, 256, 192)])
 def test_gemm_store_vs_fp64(M, N, K):
     from physdock_b200 import ops
     g = torch.Generator().manual_seed(M + N + K)
