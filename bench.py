@@ -149,7 +149,7 @@ def time_attention_kernel(dit, B, iters=12):
     H, S = 4, dit._complex_keep["Na"]
     S_pad = ops.pad_len(S)
     g = torch.Generator(device=dev).manual_seed(0)
-    planes = [torch.randn(B, H, S_pad, 32, generator=g, device=dev).half() for _ in range(6)]
+    planes = [torch.randn(B, H, S_pad, 64, generator=g, device=dev).half() for _ in range(3)]
     bias = dit._complex_keep["bias_a"].view(-1, H, S_pad, S_pad)
     for l in range(3):
         ops.attention(*planes, bias[l % bias.shape[0]])

@@ -144,12 +144,12 @@ int pdk_op_gemm_gate_resid(const void* Ah, const void* Al, int64_t lda, const vo
                            int64_t gate_stride, int64_t rows_per_sample, float* x, int64_t ldx, void* stream);
 int pdk_op_gemm_swiglu(const void* Ah, const void* Al, int64_t lda, const void* Wh, const void* Wl, int64_t ldw,
                        int64_t M, int64_t N, int64_t K, void* ph, void* pl, int64_t ldp, void* stream);
+/* q, k, v: fp16 [B,H,S_pad,64], each row = [hi 32 | lo 32] (the two split planes interleaved: 128-byte rows) */
 int pdk_op_gemm_qkv(const void* Ah, const void* Al, int64_t lda, const void* Wh, const void* Wl, int64_t ldw,
                     int64_t M, int64_t c, const float* norm_q, const float* norm_k, float rms_eps, float q_scale,
-                    int64_t rows_per_sample, void* qh, void* ql, void* kh, void* kl, void* vh, void* vl,
-                    void* stream);
-int pdk_op_attention(const void* qh, const void* ql, const void* kh, const void* kl, const void* vh, const void* vl,
-                     const float* bias, void* oh, void* ol, int64_t B, int64_t H, int64_t S_pad, void* stream);
+                    int64_t rows_per_sample, void* q, void* k, void* v, void* stream);
+int pdk_op_attention(const void* q, const void* k, const void* v, const float* bias, void* oh, void* ol, int64_t B,
+                     int64_t H, int64_t S_pad, void* stream);
 int pdk_op_precond(const float* x_hat, const float* coef, const float* a, const float* wx, const float* bx, float* ba,
                    int64_t B, int64_t Na, int64_t S_pad, int64_t c_a, void* stream);
 int pdk_op_segment_mean(const float* h, const int32_t* tok_start, const float* s, float* bs, int64_t B, int64_t Nt,

@@ -69,8 +69,8 @@ PROTOTYPES = {
                                       _vp, _i64, _vp]),
     "pdk_op_gemm_swiglu": (_int, [_vp, _vp, _i64, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _i64, _vp]),
     "pdk_op_gemm_qkv": (_int, [_vp, _vp, _i64, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _f32, _f32, _i64] +
-                        [_vp] * 6 + [_vp]),
-    "pdk_op_attention": (_int, [_vp] * 9 + [_i64, _i64, _i64, _vp]),
+                        [_vp] * 3 + [_vp]),
+    "pdk_op_attention": (_int, [_vp] * 6 + [_i64, _i64, _i64, _vp]),
     "pdk_op_precond": (_int, [_vp] * 6 + [_i64] * 4 + [_vp]),
     "pdk_op_segment_mean": (_int, [_vp] * 4 + [_i64] * 5 + [_vp]),
     "pdk_op_gather_add": (_int, [_vp] * 3 + [_i64] * 5 + [_vp]),

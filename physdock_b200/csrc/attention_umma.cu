@@ -8,9 +8,11 @@
 // is TMA-loaded once per key tile and read by all of them from shared memory, which divides the dominant L2
 // stream (bias, 4 B per score) by the group size.  Work unit u = (key tile j of 64 keys, sample g).
 //
-//   warp 8  TMA producer   : Q planes of the group (once); per key tile the bias tile [128 x 64] fp32 (two
-//                            SWIZZLE_128B boxes, double buffered) and per unit K_hi,K_lo,V_hi,V_lo [64 x 32] fp16
-//                            (SWIZZLE_64B, 6-stage ring)
+//   warp 8  TMA producer   : Q of the group (once); per key tile the bias tile [128 x 64] fp32 (two SWIZZLE_128B
+//                            boxes, double buffered) and per unit K, V [64 keys x 64 halves] (6-stage ring).  q/k/v
+//                            rows are stored interleaved [hi 32 | lo 32] = 128 bytes because TMA boxes narrower than
+//                            128 B run at less than half rate (tests/cuda/umma_probe.cu test 7); the hi and lo K=16
+//                            slices of a row are then just byte offsets 0/32 and 64/96 into a SWIZZLE_128B tile.
 //   warp 9  QK issuer      : S_g = Q_g K^T   (SS, M128 N64 K16 x 2 slices x 3 split products) into TMEM buffer g
 //   warp 10 PV issuer      : O_g += P_g V    (TS: P from TMEM, V MN-major from smem; 4 slices x 3 products)
 //                            Two issuing warps because one warp's serialized waits/commits left the tensor pipe
@@ -33,13 +35,13 @@ namespace {
 constexpr int G = 4;                 // samples per CTA
 constexpr int BQ = 128, BKV = 64, D = kHeadDim;
 constexpr int NS = 6;                // K/V ring stages
-constexpr int Q_PLANE = BQ * D * 2;                  // 8 KB
-constexpr int KV_PLANE = BKV * D * 2;                // 4 KB
-constexpr int KV_STAGE = 4 * KV_PLANE;               // 16 KB
+constexpr int Q_TILE = BQ * 2 * D * 2;               // 16 KB: 128 rows x [hi|lo] 128 B
+constexpr int KV_TILE = BKV * 2 * D * 2;             // 8 KB: 64 rows x 128 B
+constexpr int KV_STAGE = 2 * KV_TILE;                // K, V
 constexpr int BIAS_HALF = BQ * 32 * 4;               // 16 KB: [128 rows][32 fp32]
 constexpr int BIAS_TILE = 2 * BIAS_HALF;             // 32 KB
 constexpr int OFF_Q = 0;
-constexpr int OFF_BIAS = G * 2 * Q_PLANE;            // 64 KB
+constexpr int OFF_BIAS = G * Q_TILE;                 // 64 KB
 constexpr int OFF_KV = OFF_BIAS + 2 * BIAS_TILE;     // 128 KB
 constexpr int SMEM_BYTES = OFF_KV + NS * KV_STAGE + 1024;   // 225 KB
 constexpr int NTHREADS = 352;
@@ -107,10 +109,8 @@ PDK_DEV void split2_pos(float p0, float p1, uint32_t& hi, uint32_t& lo) {
 }
 
 __global__ void __launch_bounds__(NTHREADS, 1)
-attention_umma_kernel(const __grid_constant__ CUtensorMap mQh, const __grid_constant__ CUtensorMap mQl,
-                      const __grid_constant__ CUtensorMap mKh, const __grid_constant__ CUtensorMap mKl,
-                      const __grid_constant__ CUtensorMap mVh, const __grid_constant__ CUtensorMap mVl,
-                      const __grid_constant__ CUtensorMap mBias, const AttnArgs p) {
+attention_umma_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUtensorMap mK,
+                      const __grid_constant__ CUtensorMap mV, const __grid_constant__ CUtensorMap mBias, const AttnArgs p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) Bars bars;
     __shared__ uint32_t tmem_slot;
@@ -141,14 +141,11 @@ attention_umma_kernel(const __grid_constant__ CUtensorMap mQh, const __grid_cons
     if (warp == 8) {
         // ================================================================= TMA producer
         if (elect_one()) {
-            tma_prefetch_desc(&mQh); tma_prefetch_desc(&mKh); tma_prefetch_desc(&mVh); tma_prefetch_desc(&mBias);
+            tma_prefetch_desc(&mQ); tma_prefetch_desc(&mK); tma_prefetch_desc(&mV); tma_prefetch_desc(&mBias);
             const uint32_t qbar = smem_u32(&bars.q_full);
-            mbar_expect_tx(qbar, ng * 2 * Q_PLANE);
-            for (int g = 0; g < ng; ++g) {
-                const int row = ((b0 + g) * p.H + h) * S + qt * BQ;
-                tma_load_2d(sm + OFF_Q + g * 2 * Q_PLANE, &mQh, qbar, 0, row);
-                tma_load_2d(sm + OFF_Q + g * 2 * Q_PLANE + Q_PLANE, &mQl, qbar, 0, row);
-            }
+            mbar_expect_tx(qbar, ng * Q_TILE);
+            for (int g = 0; g < ng; ++g)
+                tma_load_2d(sm + OFF_Q + g * Q_TILE, &mQ, qbar, 0, ((b0 + g) * p.H + h) * S + qt * BQ);
         }
         __syncwarp();
         int st = 0;
@@ -170,10 +167,8 @@ attention_umma_kernel(const __grid_constant__ CUtensorMap mQh, const __grid_cons
                     mbar_expect_tx(kbar, KV_STAGE);
                     const int row = ((b0 + g) * p.H + h) * S + j * BKV;
                     const uint32_t dst = sm + OFF_KV + st * KV_STAGE;
-                    tma_load_2d(dst, &mKh, kbar, 0, row);
-                    tma_load_2d(dst + KV_PLANE, &mKl, kbar, 0, row);
-                    tma_load_2d(dst + 2 * KV_PLANE, &mVh, kbar, 0, row);
-                    tma_load_2d(dst + 3 * KV_PLANE, &mVl, kbar, 0, row);
+                    tma_load_2d(dst, &mK, kbar, 0, row);
+                    tma_load_2d(dst + KV_TILE, &mV, kbar, 0, row);
                 }
                 __syncwarp();
                 if (++st == NS) { st = 0; kv_par ^= 1u; }
@@ -192,9 +187,10 @@ attention_umma_kernel(const __grid_constant__ CUtensorMap mQh, const __grid_cons
                 if (j > 0) mbar_wait(smem_u32(&bars.pv_done[g]), (uint32_t)(j - 1) & 1u);
                 tc_fence_after();
                 if (elect_one()) {
-                    const uint32_t q = sm + OFF_Q + g * 2 * Q_PLANE, k = sm + OFF_KV + st * KV_STAGE;
-                    const uint64_t qh = smem_desc(q, 512, kLayoutSw64), ql = smem_desc(q + Q_PLANE, 512, kLayoutSw64);
-                    const uint64_t kh = smem_desc(k, 512, kLayoutSw64), kl = smem_desc(k + KV_PLANE, 512, kLayoutSw64);
+                    const uint32_t q = sm + OFF_Q + g * Q_TILE, k = sm + OFF_KV + st * KV_STAGE;
+                    // K-major SWIZZLE_128B tiles; hi halves at byte 0 of each row, lo halves at byte 64
+                    const uint64_t qh = smem_desc(q, 1024, kLayoutSw128), ql = smem_desc(q + 64, 1024, kLayoutSw128);
+                    const uint64_t kh = smem_desc(k, 1024, kLayoutSw128), kl = smem_desc(k + 64, 1024, kLayoutSw128);
                     const uint32_t d = tmem + COL_S + g * BKV;
 #pragma unroll
                     for (int ks = 0; ks < 2; ++ks) {
@@ -213,9 +209,9 @@ attention_umma_kernel(const __grid_constant__ CUtensorMap mQh, const __grid_cons
     } else if (warp == 10) {
         // ================================================================= PV issuer
         // O_g += P_g(j) V_g(j): P from TMEM (written by the softmax threads over S), V MN-major from smem.
-        // The V_hi and V_lo tiles sit back to back in the stage, so one MN-major descriptor with LBO = tile size
-        // presents [V_hi | V_lo] as a single N = 64 operand: P_hi [V_hi|V_lo] is one MMA (O columns 0-31 and 32-63),
-        // P_lo V_hi a second one onto columns 0-31.  2 MMAs per slice instead of 3 (every M128 MMA costs >= 45 cycles).
+        // A V row is [V_hi 32 | V_lo 32], i.e. the MN-major SWIZZLE_128B tile IS the N = 64 operand [V_hi | V_lo]:
+        // P_hi [V_hi|V_lo] is one MMA (O columns 0-31 and 32-63), P_lo V_hi a second one (N = 32 sub-read of the same
+        // tile) onto columns 0-31.  2 MMAs per slice instead of 3 (every M128 MMA costs >= 45 cycles).
         constexpr uint32_t idesc_pv = umma_idesc_f16(BQ, D, true);      // M128 N32, B (= V) MN-major
         constexpr uint32_t idesc_pv2 = umma_idesc_f16(BQ, 2 * D, true); // M128 N64
         int g = 0, st = 0;
@@ -227,15 +223,13 @@ attention_umma_kernel(const __grid_constant__ CUtensorMap mQh, const __grid_cons
                 TRACE(j * ng + g, 0);                          // PV warp saw p_ready
                 tc_fence_after();
                 if (elect_one()) {
-                    const uint32_t v = sm + OFF_KV + st * KV_STAGE + 2 * KV_PLANE;
-                    const uint64_t vh = smem_desc(v, 512, kLayoutSw64);
-                    const uint64_t vcat = smem_desc_lbo(v, KV_PLANE, 512, kLayoutSw64);
+                    const uint64_t vd = smem_desc(sm + OFF_KV + st * KV_STAGE + KV_TILE, 1024, kLayoutSw128);
                     const uint32_t pa = tmem + COL_S + g * BKV, d = tmem + COL_O + g * 2 * D;
 #pragma unroll
                     for (int ks = 0; ks < BKV / 16; ++ks) {
-                        const uint64_t o = (uint64_t)((ks * 16 * 64) >> 4);     // 16 key rows of 64 bytes
-                        umma_f16_ts(d, pa + ks * 8, vcat + o, idesc_pv2, (j | ks) != 0);    // P_hi [V_hi | V_lo]
-                        umma_f16_ts(d, pa + 32 + ks * 8, vh + o, idesc_pv, 1u);             // P_lo V_hi
+                        const uint64_t o = (uint64_t)((ks * 16 * 128) >> 4);    // 16 key rows of 128 bytes
+                        umma_f16_ts(d, pa + ks * 8, vd + o, idesc_pv2, (j | ks) != 0);      // P_hi [V_hi | V_lo]
+                        umma_f16_ts(d, pa + 32 + ks * 8, vd + o, idesc_pv, 1u);             // P_lo V_hi
                     }
                     umma_commit(smem_u32(&bars.kv_empty[st]));
                     umma_commit(smem_u32(&bars.pv_done[g]));
@@ -389,17 +383,14 @@ cudaError_t launch_attention(const AttnArgs& a_in, cudaStream_t st) {
         configured = true;
     }
     const uint64_t rows = (uint64_t)a.B * a.H * a.S_pad;
-    CUtensorMap mQh, mQl, mKh, mKl, mVh, mVl, mBias;
+    CUtensorMap mQ, mK, mV, mBias;
     cudaError_t e;
-    if ((e = get_tensor_map_f16(a.qh, rows, D, D, BQ, D, 64, &mQh)) != cudaSuccess) return e;
-    if ((e = get_tensor_map_f16(a.ql, rows, D, D, BQ, D, 64, &mQl)) != cudaSuccess) return e;
-    if ((e = get_tensor_map_f16(a.kh, rows, D, D, BKV, D, 64, &mKh)) != cudaSuccess) return e;
-    if ((e = get_tensor_map_f16(a.kl, rows, D, D, BKV, D, 64, &mKl)) != cudaSuccess) return e;
-    if ((e = get_tensor_map_f16(a.vh, rows, D, D, BKV, D, 64, &mVh)) != cudaSuccess) return e;
-    if ((e = get_tensor_map_f16(a.vl, rows, D, D, BKV, D, 64, &mVl)) != cudaSuccess) return e;
+    if ((e = get_tensor_map_f16(a.q, rows, 2 * D, 2 * D, BQ, 2 * D, 128, &mQ)) != cudaSuccess) return e;
+    if ((e = get_tensor_map_f16(a.k, rows, 2 * D, 2 * D, BKV, 2 * D, 128, &mK)) != cudaSuccess) return e;
+    if ((e = get_tensor_map_f16(a.v, rows, 2 * D, 2 * D, BKV, 2 * D, 128, &mV)) != cudaSuccess) return e;
     if ((e = get_tensor_map_f32(a.bias, (uint64_t)a.H * a.S_pad, a.S_pad, a.S_pad, BQ, 32, 128, &mBias)) != cudaSuccess) return e;
     dim3 grid((a.B + G - 1) / G, a.S_pad / BQ, a.H);
-    attention_umma_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(mQh, mQl, mKh, mKl, mVh, mVl, mBias, a);
+    attention_umma_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(mQ, mK, mV, mBias, a);
     return cudaGetLastError();
 }
 

@@ -60,7 +60,7 @@ namespace {
 
 struct Workspace {
     float *coef, *tsilu, *mod, *ba, *bs, *down, *up;
-    __half *xh, *xl, *qh, *ql, *kh, *kl, *vh, *vl, *oh, *ol, *hh, *hl;
+    __half *xh, *xl, *q, *k, *v, *oh, *ol, *hh, *hl;
     size_t bytes;
 };
 
@@ -83,8 +83,10 @@ Workspace carve(const pdk_dit& h, int64_t B, int64_t Sa, int64_t St, uint8_t* ba
     w.bs = (float*)take(Mt * h.d.c_s * 4);
     w.down = (float*)take(Ma * h.d.c_s * 4);
     w.up = (float*)take(Mt * h.d.c_a * 4);
-    __half** planes[] = {&w.xh, &w.xl, &w.qh, &w.ql, &w.kh, &w.kl, &w.vh, &w.vl, &w.oh, &w.ol};
+    __half** planes[] = {&w.xh, &w.xl, &w.oh, &w.ol};
     for (auto pp : planes) *pp = (__half*)take(act * 2);
+    __half** qkv[] = {&w.q, &w.k, &w.v};                 // interleaved [hi|lo]: twice the halves
+    for (auto pp : qkv) *pp = (__half*)take(act * 4);
     w.hh = (__half*)take(hid * 2);
     w.hl = (__half*)take(hid * 2);
     w.bytes = off;
@@ -106,11 +108,11 @@ int run_block(const pdk_dit& h, const pdk_block_weights& bw, const Workspace& ws
     g.Ah = ws.xh; g.Al = ws.xl; g.lda = c;
     g.Wh = H(bw.wqkv_h); g.Wl = H(bw.wqkv_l); g.ldw = c;
     g.M = M; g.N = 3 * c; g.K = c;
-    g.qh = ws.qh; g.ql = ws.ql; g.kh = ws.kh; g.kl = ws.kl; g.vh = ws.vh; g.vl = ws.vl;
+    g.q = ws.q; g.k = ws.k; g.v = ws.v;
     g.norm_q = bw.norm_q; g.norm_k = bw.norm_k; g.c = c; g.rows_per_sample = (int)Sp;
     g.rms_eps = eps; g.q_scale = kLog2e / sqrtf((float)kHeadDim);
     PDK_TRY("gemm(qkv)", launch_gemm(EPI_QKV, g, st));
-    AttnArgs at{ws.qh, ws.ql, ws.kh, ws.kl, ws.vh, ws.vl, bias, ws.oh, ws.ol, (int)B, Hh, (int)Sp, c, nullptr};
+    AttnArgs at{ws.q, ws.k, ws.v, bias, ws.oh, ws.ol, (int)B, Hh, (int)Sp, c, nullptr};
     PDK_TRY("attention", launch_attention(at, st));
     g = GemmArgs{};
     g.Ah = ws.oh; g.Al = ws.ol; g.lda = c;
@@ -382,17 +384,17 @@ int pdk_op_gemm_swiglu(const void* Ah, const void* Al, int64_t lda, const void* 
 }
 int pdk_op_gemm_qkv(const void* Ah, const void* Al, int64_t lda, const void* Wh, const void* Wl, int64_t ldw, int64_t M,
                     int64_t c, const float* norm_q, const float* norm_k, float rms_eps, float q_scale,
-                    int64_t rows_per_sample, void* qh, void* ql, void* kh, void* kl, void* vh, void* vl, void* stream) {
+                    int64_t rows_per_sample, void* q, void* k, void* v, void* stream) {
     GemmArgs g = base_args(Ah, Al, lda, Wh, Wl, ldw, M, 3 * c, c);
     g.norm_q = norm_q; g.norm_k = norm_k; g.c = (int)c; g.rms_eps = rms_eps; g.q_scale = q_scale;
     g.rows_per_sample = (int)rows_per_sample;
-    g.qh = H(qh); g.ql = H(ql); g.kh = H(kh); g.kl = H(kl); g.vh = H(vh); g.vl = H(vl);
+    g.q = H(q); g.k = H(k); g.v = H(v);
     PDK_TRY("gemm_qkv", launch_gemm(EPI_QKV, g, S(stream)));
     return 0;
 }
-int pdk_op_attention(const void* qh, const void* ql, const void* kh, const void* kl, const void* vh, const void* vl,
-                     const float* bias, void* oh, void* ol, int64_t B, int64_t Hh, int64_t S_pad, void* stream) {
-    AttnArgs a{H(qh), H(ql), H(kh), H(kl), H(vh), H(vl), bias, H(oh), H(ol), (int)B, (int)Hh, (int)S_pad, (int)(Hh * kHeadDim), nullptr};
+int pdk_op_attention(const void* q, const void* k, const void* v, const float* bias, void* oh, void* ol, int64_t B,
+                     int64_t Hh, int64_t S_pad, void* stream) {
+    AttnArgs a{H(q), H(k), H(v), bias, H(oh), H(ol), (int)B, (int)Hh, (int)S_pad, (int)(Hh * kHeadDim), nullptr};
     PDK_TRY("attention", launch_attention(a, S(stream)));
     return 0;
 }

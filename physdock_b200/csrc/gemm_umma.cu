@@ -204,10 +204,10 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant_
 #pragma unroll
                         for (int i = 0; i < 32; ++i) v[i] = v[i] * inv * __ldg(gain + i);
                     }
-                    __half* dh = which == 0 ? p.qh : (which == 1 ? p.kh : p.vh);
-                    __half* dl = which == 0 ? p.ql : (which == 1 ? p.kl : p.vl);
+                    __half* dh = which == 0 ? p.q : (which == 1 ? p.k : p.v);      // row = [hi 32 | lo 32] halves
+                    __half* dl = dh + kHeadDim;
                     const size_t d0 = ((size_t)((row / p.rows_per_sample) * H + head) * p.rows_per_sample +
-                                       (row % p.rows_per_sample)) * kHeadDim;
+                                       (row % p.rows_per_sample)) * (2 * kHeadDim);
                     uint32_t hi[16], lo[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) split2(v[2 * i], v[2 * i + 1], hi[i], lo[i]);

@@ -13,7 +13,7 @@ enum GemmEpilogue {
     EPI_STORE = 0,       // out[M,N] (fp32) = act(acc + bias)
     EPI_GATE_RESID = 1,  // out[M,N] (fp32, in place) += (acc + bias) * gate[sample(row)][col]
     EPI_SWIGLU = 2,      // W rows interleaved in blocks of 16 (w1 | w3): planes[M, N/2] = split(silu(h1) * h3)
-    EPI_QKV = 3,         // N = 3c: per-head RMSNorm on q and k, q pre-scaled, planes [B,H,S_pad,32]
+    EPI_QKV = 3,         // N = 3c: per-head RMSNorm on q and k, q pre-scaled, interleaved planes [B,H,S_pad,64]
 };
 
 struct GemmArgs {
@@ -27,7 +27,7 @@ struct GemmArgs {
     int gate_stride;
     int rows_per_sample;        // S_pad (EPI_GATE_RESID, EPI_QKV)
     __half* ph; __half* pl; int ldp;   // EPI_SWIGLU output planes [M, N/2]
-    __half* qh; __half* ql; __half* kh; __half* kl; __half* vh; __half* vl;   // EPI_QKV
+    __half* q; __half* k; __half* v;   // EPI_QKV: [B,H,S_pad,64] rows = [hi 32 | lo 32] (128-byte rows for TMA)
     const float* norm_q; const float* norm_k;   // [32] RMSNorm gains
     int c;                      // model width (N == 3c)
     float rms_eps; float q_scale;
@@ -35,10 +35,10 @@ struct GemmArgs {
 cudaError_t launch_gemm(GemmEpilogue epi, const GemmArgs& a, cudaStream_t st);
 
 // ----------------------------------------------------------------------------- pair-bias attention
-// q,k,v planes [B,H,S_pad,32] (q pre-scaled by log2e/sqrt(32)); bias [H,S_pad,S_pad] fp32 (pre-scaled by
-// log2e, pad columns = kPadBias); output planes o[B*S_pad, c] with column h*32+d.
+// q,k,v [B,H,S_pad,64] with rows [hi 32 | lo 32] (q pre-scaled by log2e/sqrt(32)); bias [H,S_pad,S_pad] fp32
+// (pre-scaled by log2e, pad columns = kPadBias); output planes o[B*S_pad, c] with column h*32+d.
 struct AttnArgs {
-    const __half* qh; const __half* ql; const __half* kh; const __half* kl; const __half* vh; const __half* vl;
+    const __half* q; const __half* k; const __half* v;
     const float* bias;
     __half* oh; __half* ol;
     int B, H, S_pad, c;

@@ -108,12 +108,22 @@ def gemm_swiglu(ah, al, w13h, w13l):
     return ph, pl
 
 
+def interleave_planes(x: torch.Tensor) -> torch.Tensor:
+    """fp32 [..., 32] -> fp16 [..., 64] with rows [hi 32 | lo 32] (the q/k/v operand layout of the attention kernel)."""
+    hi, lo = split_planes(x)
+    return torch.cat([hi, lo], dim=-1).contiguous()
+
+
+def deinterleave_to_float(t: torch.Tensor) -> torch.Tensor:
+    return t[..., :32].float() + t[..., 32:].float()
+
+
 def gemm_qkv(ah, al, wh, wl, norm_q, norm_k, rms_eps: float, B: int, S_pad: int):
-    """-> six planes [B,H,S_pad,32]; q is RMS-normed and pre-scaled by log2e/sqrt(32), k RMS-normed."""
+    """-> q, k, v fp16 [B,H,S_pad,64] (rows [hi|lo]); q is RMS-normed and pre-scaled by log2e/sqrt(32), k RMS-normed."""
     lib = _lib.load()
     M, c = ah.shape
     H = c // 32
-    outs = [torch.empty(B, H, S_pad, 32, dtype=torch.float16, device=ah.device) for _ in range(6)]
+    outs = [torch.empty(B, H, S_pad, 64, dtype=torch.float16, device=ah.device) for _ in range(3)]
     _lib.check(lib.pdk_op_gemm_qkv(_lib.ptr(ah), _lib.ptr(al), c, _lib.ptr(wh), _lib.ptr(wl), c, M, c,
                                    _lib.ptr(norm_q.contiguous()), _lib.ptr(norm_k.contiguous()), rms_eps,
                                    LOG2E / math.sqrt(32.0), S_pad, *[_lib.ptr(o) for o in outs],
@@ -121,14 +131,14 @@ def gemm_qkv(ah, al, wh, wl, norm_q, norm_k, rms_eps: float, B: int, S_pad: int)
     return outs
 
 
-def attention(qh, ql, kh, kl, vh, vl, bias):
-    """planes [B,H,S_pad,32] + bias [H,S_pad,S_pad] (log2 domain) -> o planes [B*S_pad, H*32]."""
+def attention(q, k, v, bias):
+    """q,k,v fp16 [B,H,S_pad,64] (rows [hi|lo]) + bias [H,S_pad,S_pad] (log2 domain) -> o planes [B*S_pad, H*32]."""
     lib = _lib.load()
-    B, H, S_pad, _ = qh.shape
-    oh = torch.empty(B * S_pad, H * 32, dtype=torch.float16, device=qh.device)
+    B, H, S_pad, _ = q.shape
+    oh = torch.empty(B * S_pad, H * 32, dtype=torch.float16, device=q.device)
     ol = torch.empty_like(oh)
-    _lib.check(lib.pdk_op_attention(*[_lib.ptr(t) for t in (qh, ql, kh, kl, vh, vl)], _lib.ptr(bias.contiguous()),
-                                    _lib.ptr(oh), _lib.ptr(ol), B, H, S_pad, _lib.stream_ptr(qh.device)), "attention")
+    _lib.check(lib.pdk_op_attention(_lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(bias.contiguous()),
+                                    _lib.ptr(oh), _lib.ptr(ol), B, H, S_pad, _lib.stream_ptr(q.device)), "attention")
     return oh, ol
 
 

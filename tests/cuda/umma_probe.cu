@@ -545,6 +545,90 @@ static void run_mc(EncodeFn enc, __half* buf, int rows_total, long long* dout) {
            (double)iters * 32768 / avg, (double)iters * 32768 / C / avg, avg / iters);
 }
 
+
+// ---- test 9: interleaved operands.  Q,K rows = [hi 32 | lo 32] halves (128 B, K-major SWIZZLE_128B): S = Qh Kh^T + Qh Kl^T + Ql Kh^T
+// by pointing the K=16 slices at byte offsets 0/32 (hi) and 64/96 (lo).  V rows = [Vh 32 | Vl 32] (MN-major SWIZZLE_128B):
+// O = Ph [Vh|Vl] (N=64) + Pl Vh (N=32 sub-read of the same tile), P from TMEM.  D0 = S [128x128], D1 = O [128x32].
+__global__ void __launch_bounds__(128) probe_il_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
+                                                       const __grid_constant__ CUtensorMap mapV, const float* __restrict__ P,
+                                                       float* __restrict__ Sout, float* __restrict__ Oout) {
+    extern __shared__ __align__(1024) uint8_t smem_[];
+    __shared__ __align__(8) uint64_t bars[2];
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const uint32_t smem = (smem_u32(smem_) + 1023u) & ~1023u;
+    const uint32_t bar_tma = smem_u32(&bars[0]), bar_mma = smem_u32(&bars[1]);
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    if (tid == 0) { mbar_init(bar_tma, 1); mbar_init(bar_mma, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_base_s;
+    const uint32_t sQ = smem, sK = smem + 16384, sV = smem + 32768;     // each 128 rows x 128 B = 16 KB
+    if (tid == 0) {
+        mbar_expect_tx(bar_tma, 3 * 16384);
+        tma_load_2d(sQ, &mapQ, bar_tma, 0, 0);
+        tma_load_2d(sK, &mapK, bar_tma, 0, 0);
+        tma_load_2d(sV, &mapV, bar_tma, 0, 0);
+    }
+    const float* prow = P + (size_t)tid * 128;
+    for (int half = 0; half < 2; ++half) {
+        uint32_t hi[32], lo[32];
+        for (int i = 0; i < 32; ++i) {
+            const float x0 = prow[half * 64 + 2 * i], x1 = prow[half * 64 + 2 * i + 1];
+            __half2 h = __floats2half2_rn(x0, x1);
+            float2 hf = __half22float2(h);
+            __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+            hi[i] = *reinterpret_cast<uint32_t*>(&h);
+            lo[i] = *reinterpret_cast<uint32_t*>(&l);
+        }
+        tmem_st32(tmem + ((uint32_t)(warp * 32) << 16) + half * 32, hi);          // P_hi cols [0,64)
+        tmem_st32(tmem + ((uint32_t)(warp * 32) << 16) + 64 + half * 32, lo);     // P_lo cols [64,128)
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    mbar_wait(bar_tma, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (tid == 0) {
+        const uint32_t hb = ((1024u >> 4) & 0x3FFF) | (1u << 14) | (2u << 29);     // SBO 1024, SWIZZLE_128B
+        auto desc = [&](uint32_t a) { return ((uint64_t)hb << 32) | (1ull << 16) | (uint64_t)((a >> 4) & 0x3FFF); };
+        const uint32_t id_qk = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t id_pv64 = (1u << 4) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t id_pv32 = (1u << 4) | (1u << 16) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t dS = tmem + 128, dO = tmem + 256;
+        for (int ks = 0; ks < 2; ++ks) {
+            umma_f16(dS, desc(sQ + 64 + ks * 32), desc(sK + ks * 32), id_qk, ks != 0);        // Ql Kh
+            umma_f16(dS, desc(sQ + ks * 32), desc(sK + 64 + ks * 32), id_qk, 1u);             // Qh Kl
+            umma_f16(dS, desc(sQ + ks * 32), desc(sK + ks * 32), id_qk, 1u);                  // Qh Kh
+        }
+        for (int k = 0; k < 8; ++k) {      // 16 kv rows of 128 B per slice
+            umma_f16_ts(dO, tmem + k * 8, desc(sV + k * 2048), id_pv64, k != 0);              // Ph [Vh|Vl]
+            umma_f16_ts(dO, tmem + 64 + k * 8, desc(sV + k * 2048), id_pv32, 1u);             // Pl Vh
+        }
+        umma_commit(bar_mma);
+    }
+    mbar_wait(bar_mma, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    for (int c0 = 0; c0 < 128; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32p(tmem + ((uint32_t)(warp * 32) << 16) + 128 + c0, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        for (int i = 0; i < 32; ++i) Sout[(size_t)tid * 128 + c0 + i] = __uint_as_float(v[i]);
+    }
+    uint32_t v[32], v2[32];
+    tmem_ld32p(tmem + ((uint32_t)(warp * 32) << 16) + 256, v);
+    tmem_ld32p(tmem + ((uint32_t)(warp * 32) << 16) + 288, v2);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    for (int i = 0; i < 32; ++i) Oout[(size_t)tid * 32 + i] = __uint_as_float(v[i]) + __uint_as_float(v2[i]);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+}
+
 static uint32_t desc_hi(uint32_t sbo_bytes, uint32_t layout_type) {
     return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | (layout_type << 29);   // SBO | version=1 (bit 46) | layout (bits 61..63)
 }
@@ -589,6 +673,58 @@ int main(int argc, char** argv) {
 
 
 
+
+    if (test == 9) {
+        std::vector<float> Q(128 * 32), K(128 * 32), V(128 * 32), Pm(128 * 128);
+        srand(99);
+        for (auto& v : Q) v = (rand() % 2001 - 1000) / 400.0f;
+        for (auto& v : K) v = (rand() % 2001 - 1000) / 400.0f;
+        for (auto& v : V) v = (rand() % 2001 - 1000) / 500.0f;
+        for (auto& v : Pm) v = (rand() % 10001) / 10000.0f * (rand() % 7 == 0 ? 1.0f : 0.01f);
+        auto interleave = [](const std::vector<float>& x) {        // [128][hi 32 | lo 32]
+            std::vector<__half> o(128 * 64);
+            for (int r = 0; r < 128; ++r)
+                for (int c = 0; c < 32; ++c) {
+                    const __half h = __float2half_rn(x[r * 32 + c]);
+                    o[r * 64 + c] = h;
+                    o[r * 64 + 32 + c] = __float2half_rn(x[r * 32 + c] - __half2float(h));
+                }
+            return o;
+        };
+        auto Qi = interleave(Q), Ki = interleave(K), Vi = interleave(V);
+        __half *dQ, *dK, *dV; float *dP, *dS, *dO;
+        CK(cudaMalloc(&dQ, 16384)); CK(cudaMalloc(&dK, 16384)); CK(cudaMalloc(&dV, 16384));
+        CK(cudaMalloc(&dP, Pm.size() * 4)); CK(cudaMalloc(&dS, 128 * 128 * 4)); CK(cudaMalloc(&dO, 128 * 32 * 4));
+        CK(cudaMemcpy(dQ, Qi.data(), 16384, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dK, Ki.data(), 16384, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(dV, Vi.data(), 16384, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dP, Pm.data(), Pm.size() * 4, cudaMemcpyHostToDevice));
+        CUtensorMap mQ = make_map(enc, dQ, 128, 64, 128, 64, CU_TENSOR_MAP_SWIZZLE_128B);
+        CUtensorMap mK = make_map(enc, dK, 128, 64, 128, 64, CU_TENSOR_MAP_SWIZZLE_128B);
+        CUtensorMap mV = make_map(enc, dV, 128, 64, 128, 64, CU_TENSOR_MAP_SWIZZLE_128B);
+        CK(cudaFuncSetAttribute(probe_il_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 49152 + 1024));
+        probe_il_kernel<<<1, 128, 49152 + 1024>>>(mQ, mK, mV, dP, dS, dO);
+        CK(cudaGetLastError());
+        CK(cudaDeviceSynchronize());
+        std::vector<float> Sm(128 * 128), Om(128 * 32);
+        CK(cudaMemcpy(Sm.data(), dS, Sm.size() * 4, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(Om.data(), dO, Om.size() * 4, cudaMemcpyDeviceToHost));
+        double es = 0, rs = 0, eo = 0, ro = 0;
+        for (int i = 0; i < 128; ++i) {
+            for (int j = 0; j < 128; ++j) {
+                double ref = 0;
+                for (int k = 0; k < 32; ++k) ref += (double)Q[i * 32 + k] * (double)K[j * 32 + k];
+                es = fmax(es, fabs(ref - Sm[i * 128 + j])); rs = fmax(rs, fabs(ref));
+            }
+            for (int j = 0; j < 32; ++j) {
+                double ref = 0;
+                for (int k = 0; k < 128; ++k) ref += (double)Pm[i * 128 + k] * (double)V[k * 32 + j];
+                eo = fmax(eo, fabs(ref - Om[i * 32 + j])); ro = fmax(ro, fabs(ref));
+            }
+        }
+        const bool ps = es <= 2e-5 * rs + 1e-6, po = eo <= 2e-5 * ro + 1e-6;
+        printf("PROBE test=9 interleaved QK: max_err=%.3e (ref %.2f) %s | interleaved PV: max_err=%.3e (ref %.2f) %s\n", es, rs,
+               ps ? "PASS" : "FAIL", eo, ro, po ? "PASS" : "FAIL");
+        return (ps && po) ? 0 : 1;
+    }
     if (test == 8) {
         long long* dout; CK(cudaMalloc(&dout, 2048 * 8));
         const int rows_total = 1 << 23;

@@ -60,7 +60,7 @@ def test_attention_vs_fp64(B, H, S):
     bias = (torch.randn(H, S, S, generator=g) * 2).to(DEV)
     bias[:, :, S - 5:] = -1e9       # masked keys
     scale = ops.LOG2E / math.sqrt(32.0)
-    planes = [*ops.split_planes(q * scale), *ops.split_planes(k), *ops.split_planes(v)]
+    planes = [ops.interleave_planes(q * scale), ops.interleave_planes(k), ops.interleave_planes(v)]
     oh, ol = ops.attention(*planes, (bias * ops.LOG2E).contiguous())
     got = ops.planes_to_float(oh, ol).view(B, S, H, 32).transpose(1, 2)
     want = torch.softmax(q.double() @ k.double().transpose(-1, -2) / math.sqrt(32.0) + bias.double(), -1) @ v.double()
@@ -147,7 +147,7 @@ def test_qkv_epilogue(env):
             y = O.rms_norm(y, sd[p + f"norm_{n}.weight"], dims.eps)
         want[n] = y * (ops.LOG2E / math.sqrt(32.0) if n == "q" else 1.0)
     for i, n in enumerate("qkv"):
-        got = ops.planes_to_float(planes[2 * i], planes[2 * i + 1])[:, :, :75]
+        got = ops.deinterleave_to_float(planes[i])[:, :, :75]
         rel_close(n, got, want[n], rtol=0, atol=3e-6 * float(want[n].abs().max()))
 
 

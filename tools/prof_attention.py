@@ -6,7 +6,7 @@ B, H, S = int(os.environ.get("B", 16)), int(os.environ.get("H", 4)), int(os.envi
 dev = torch.device("cuda")
 g = torch.Generator(device=dev).manual_seed(0)
 q, k, v = [torch.randn(B, H, S, 32, generator=g, device=dev) for _ in range(3)]
-planes = [*ops.split_planes(q * 0.25), *ops.split_planes(k), *ops.split_planes(v)]
+planes = [ops.interleave_planes(q * 0.25), ops.interleave_planes(k), ops.interleave_planes(v)]
 bias = torch.randn(3, H, S, S, generator=g, device=dev)
 for i in range(int(os.environ.get("N", 4))):
     ops.attention(*planes, bias[i % 3])

@@ -6,7 +6,7 @@ B, H, S = 16, 4, 2048
 dev = torch.device("cuda")
 g = torch.Generator(device=dev).manual_seed(0)
 q, k, v = [torch.randn(B, H, S, 32, generator=g, device=dev) for _ in range(3)]
-planes = [*ops.split_planes(q * 0.25), *ops.split_planes(k), *ops.split_planes(v)]
+planes = [ops.interleave_planes(q * 0.25), ops.interleave_planes(k), ops.interleave_planes(v)]
 bias = torch.randn(H, S, S, generator=g, device=dev)
 ops.attention(*planes, bias); torch.cuda.synchronize()
 lib = _lib.load()
