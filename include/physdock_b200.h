@@ -57,7 +57,8 @@ typedef struct {          /* one DiTBlock (transformers.py:149-159); all device 
 typedef struct {
     const float* freq;                        /* [128] exp(-ln(1e4) k/128)  (timestep_embeddings.py:62-67) */
     const float* te_w1; const float* te_b1; const float* te_w2; const float* te_b2;   /* [256,256],[256] x2 */
-    const float* wmod; const float* bmod;     /* [n_mod,256], [n_mod]: every AdaLayerNormZero.linear, concatenated */
+    const void* wmod_h; const void* wmod_l;   /* fp16 planes [n_mod,256]: every AdaLayerNormZero.linear, concatenated */
+    const float* bmod;                        /* [n_mod] */
     const float* wx; const float* bx;         /* linear_x [c_a,3],[c_a] */
     const void* wdown_h; const void* wdown_l; const float* bdown;   /* linear_downscale [c_s,c_a] */
     const void* wup_h;   const void* wup_l;   const float* bup;     /* linear_upscale   [c_a,c_s] */

@@ -36,7 +36,7 @@ class BlockWeights(C.Structure):
 
 
 class DitWeights(C.Structure):
-    _fields_ = [(n, _vp) for n in ("freq", "te_w1", "te_b1", "te_w2", "te_b2", "wmod", "bmod", "wx", "bx",
+    _fields_ = [(n, _vp) for n in ("freq", "te_w1", "te_b1", "te_w2", "te_b2", "wmod_h", "wmod_l", "bmod", "wx", "bx",
                                    "wdown_h", "wdown_l", "bdown", "wup_h", "wup_l", "bup",
                                    "norm_r_w", "norm_r_b", "wr", "wz_atom_T", "bz_atom", "wz_tok_T", "bz_tok")] + \
                [("blocks", C.POINTER(BlockWeights)), ("n_blocks", _i64)]

@@ -60,7 +60,7 @@ namespace {
 
 struct Workspace {
     float *coef, *tsilu, *mod, *ba, *bs, *down, *up;
-    __half *xh, *xl, *q, *k, *v, *oh, *ol, *hh, *hl;
+    __half *xh, *xl, *q, *k, *v, *oh, *ol, *hh, *hl, *tsh, *tsl;
     size_t bytes;
 };
 
@@ -77,8 +77,11 @@ Workspace carve(const pdk_dit& h, int64_t B, int64_t Sa, int64_t St, uint8_t* ba
     const size_t act = std::max(Ma * h.d.c_a, Mt * h.d.c_s);            // elements of the widest activation
     const size_t hid = std::max(Ma * h.d.hidden_a, Mt * h.d.hidden_s);
     w.coef = (float*)take((size_t)B * 4 * 4);
+    const size_t Bp = (size_t)pad128(B);                    // the modulation GEMM runs on 128-row tiles
     w.tsilu = (float*)take((size_t)B * kTimeDim * 4);
-    w.mod = (float*)take((size_t)B * h.d.n_mod * 4);
+    w.tsh = (__half*)take(Bp * kTimeDim * 2);
+    w.tsl = (__half*)take(Bp * kTimeDim * 2);
+    w.mod = (float*)take(Bp * h.d.n_mod * 4);
     w.ba = (float*)take(Ma * h.d.c_a * 4);
     w.bs = (float*)take(Mt * h.d.c_s * 4);
     w.down = (float*)take(Ma * h.d.c_s * 4);
@@ -156,7 +159,7 @@ int pdk_dit_create(const pdk_dit_dims* dims, pdk_dit** out) {
         return fail_msg("pdk_dit_create", "kernels are specialised for c_a=128, c_ap=16, c_s=512, c_z=128 (PhysDock/configs.py:59-63)");
     if (d.hidden_a % 32 || d.hidden_s % 32 || d.hidden_a % 64 || d.hidden_s % 64)
         return fail_msg("pdk_dit_create", "SwiGLU widths must be multiples of 64");
-    if (d.n_atom_blocks <= 0 || d.n_token_blocks <= 0 || d.n_mod <= 0 || d.n_mod % 4)
+    if (d.n_atom_blocks <= 0 || d.n_token_blocks <= 0 || d.n_mod <= 0 || d.n_mod % 128)
         return fail_msg("pdk_dit_create", "bad block counts / n_mod");
     pdk_dit* h = new (std::nothrow) pdk_dit();
     if (!h) return fail_msg("pdk_dit_create", "out of host memory");
@@ -239,9 +242,17 @@ int pdk_dit_denoise(pdk_dit* h, const float* x_hat, const float* t_hat, int64_t 
     const int nA = (int)d.n_atom_blocks, nT = (int)d.n_token_blocks;
 
     // precond (transformers.py:218-226) + all AdaLN-Zero modulations of this step
+    // ... as ONE tensor-core GEMM [pad128(B) x 256] x [n_mod x 256]^T (adaptive_layer_norm_zero.py:19, all 36 layers)
     PDK_TRY("time_embed", launch_time_embed(t_hat, h->w.freq, h->w.te_w1, h->w.te_b1, h->w.te_w2, h->w.te_b2,
-                                            (float)d.sigma_data, ws.tsilu, ws.coef, (int)B, st));
-    PDK_TRY("mod_gemv", launch_mod_gemv(ws.tsilu, h->w.wmod, h->w.bmod, ws.mod, (int)B, (int)d.n_mod, st));
+                                            (float)d.sigma_data, nullptr, ws.tsh, ws.tsl, (int)pad128(B), ws.coef, (int)B, st));
+    {
+        GemmArgs g{};
+        g.Ah = ws.tsh; g.Al = ws.tsl; g.lda = kTimeDim;
+        g.Wh = H(h->w.wmod_h); g.Wl = H(h->w.wmod_l); g.ldw = kTimeDim;
+        g.M = (int)pad128(B); g.N = (int)d.n_mod; g.K = kTimeDim;
+        g.bias = h->w.bmod; g.out = ws.mod; g.ldo = (int)d.n_mod;
+        PDK_TRY("gemm(mod)", launch_gemm(EPI_STORE, g, st));
+    }
     PDK_TRY("precond", launch_precond(x_hat, ws.coef, h->a, h->w.wx, h->w.bx, ws.ba, (int)B, (int)h->Na, (int)Sa, ca, st));
 
     // atom encoder (transformers.py:252)
@@ -333,7 +344,7 @@ int pdk_op_pair_bias(const float* pair, const float* mask, const float* wfoldT, 
 }
 int pdk_op_time_embed(const float* t_hat, const float* freq, const float* w1, const float* b1, const float* w2,
                       const float* b2, float sigma_data, float* tsilu, float* coef, int64_t B, void* stream) {
-    PDK_TRY("time_embed", launch_time_embed(t_hat, freq, w1, b1, w2, b2, sigma_data, tsilu, coef, (int)B, S(stream)));
+    PDK_TRY("time_embed", launch_time_embed(t_hat, freq, w1, b1, w2, b2, sigma_data, tsilu, nullptr, nullptr, 0, coef, (int)B, S(stream)));
     return 0;
 }
 int pdk_op_mod_gemv(const float* tsilu, const float* wmod, const float* bmod, float* mod, int64_t B, int64_t n_mod,

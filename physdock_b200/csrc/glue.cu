@@ -12,17 +12,23 @@ namespace {
 // ------------------------------------------------------------------------------------------------
 // precond scalars + TimestepEmbeddings (transformers.py:219-224, timestep_embeddings.py:35-86,127-166).
 // One CTA per sample.  The sinusoid argument t_hat*c_noise reaches ~6.5e3 rad, where a 1-ulp change of the
-// fp32 log moves the phase by ~4e-4 rad; log/sin/cos are therefore evaluated in fp64 and rounded once, which
-// reproduces a correctly rounded fp32 libm (the oracle's CPU path is within 1 ulp of that).
+// fp32 log moves the phase by ~4e-4 rad; the log is therefore evaluated in fp64 and rounded once (a correctly
+// rounded fp32 log; the oracle's CPU libm is within 1 ulp of that).  sin/cos use the accurate fp32 sincosf
+// (full-range argument reduction, <= 2 ulp): their fp64 versions cost ~45 us per step for no measurable gain.
 __global__ void __launch_bounds__(256) time_embed_kernel(const float* __restrict__ t_hat,
                                                          const float* __restrict__ freq,
                                                          const float* __restrict__ w1, const float* __restrict__ b1,
                                                          const float* __restrict__ w2, const float* __restrict__ b2,
                                                          float sigma_data, float* __restrict__ tsilu,
-                                                         float* __restrict__ coef) {
-    __shared__ float proj[kTimeDim];
-    __shared__ float hid[kTimeDim];
-    const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+                                                         __half* __restrict__ ts_h, __half* __restrict__ ts_l,
+                                                         float* __restrict__ coef, int B) {
+    __shared__ __align__(16) float proj[kTimeDim];
+    __shared__ __align__(16) float hid[kTimeDim];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    if (b >= B) {      // zero padding rows of the [128 x 256] operand planes of the modulation GEMM
+        if (ts_h != nullptr) { ts_h[(size_t)b * kTimeDim + tid] = __float2half(0.f); ts_l[(size_t)b * kTimeDim + tid] = __float2half(0.f); }
+        return;
+    }
     const float t = t_hat[b];
     const float sd2 = sigma_data * sigma_data;
     const float t2 = t * t;
@@ -36,24 +42,32 @@ __global__ void __launch_bounds__(256) time_embed_kernel(const float* __restrict
     const float t_in = t * c_noise;                                     // (:223) sic
     if (tid < 128) {
         const float arg = t_in * freq[tid];
-        proj[tid] = (float)cos((double)arg);          // flip_sin_to_cos=True -> [cos | sin]
-        proj[128 + tid] = (float)sin((double)arg);
+        float sn, cs;
+        sincosf(arg, &sn, &cs);
+        proj[tid] = cs;                               // flip_sin_to_cos=True -> [cos | sin]
+        proj[128 + tid] = sn;
     }
     __syncthreads();
-    for (int o = warp; o < kTimeDim; o += 8) {        // linear_1 + SiLU
-        float acc = 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc = fmaf(proj[lane + 32 * i], w1[(size_t)o * kTimeDim + lane + 32 * i], acc);
-        acc = warp_sum(acc);
-        if (lane == 0) hid[o] = silu(acc + b1[o]);
-    }
+    // thread = one output feature; 64 independent float4 loads per layer keep the (L2-resident) weight rows streaming
+    auto matvec = [&](const float* __restrict__ w, const float* x) {
+        const float4* row = reinterpret_cast<const float4*>(w + (size_t)tid * kTimeDim);
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 16
+        for (int k = 0; k < kTimeDim / 4; ++k) {
+            const float4 wv = __ldg(row + k);
+            const float4 xv = reinterpret_cast<const float4*>(x)[k];
+            a0 = fmaf(wv.x, xv.x, a0); a1 = fmaf(wv.y, xv.y, a1); a2 = fmaf(wv.z, xv.z, a2); a3 = fmaf(wv.w, xv.w, a3);
+        }
+        return (a0 + a1) + (a2 + a3);
+    };
+    hid[tid] = silu(matvec(w1, proj) + b1[tid]);      // linear_1 + SiLU
     __syncthreads();
-    for (int o = warp; o < kTimeDim; o += 8) {        // linear_2, then the SiLU every AdaLN applies first
-        float acc = 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc = fmaf(hid[lane + 32 * i], w2[(size_t)o * kTimeDim + lane + 32 * i], acc);
-        acc = warp_sum(acc);
-        if (lane == 0) tsilu[(size_t)b * kTimeDim + o] = silu(acc + b2[o]);
+    const float out = silu(matvec(w2, hid) + b2[tid]);   // linear_2, then the SiLU every AdaLN applies first
+    if (tsilu != nullptr) tsilu[(size_t)b * kTimeDim + tid] = out;
+    if (ts_h != nullptr) {
+        const __half h = __float2half_rn(out);
+        ts_h[(size_t)b * kTimeDim + tid] = h;
+        ts_l[(size_t)b * kTimeDim + tid] = __float2half_rn(out - __half2float(h));
     }
 }
 
@@ -61,30 +75,33 @@ __global__ void __launch_bounds__(256) time_embed_kernel(const float* __restrict
 // mod[b, n] = sum_k tsilu[b,k] * wmod[n,k] + bmod[n]: the 36 AdaLN-Zero `Linear(256 -> 3c)` of the model in
 // one weight-streaming pass (adaptive_layer_norm_zero.py:19).  Warp per output column, samples in registers.
 constexpr int MOD_BCHUNK = 16;
+constexpr int MOD_COLS = 64;       // output columns per CTA (8 per warp): amortises staging tsilu in shared memory
 __global__ void __launch_bounds__(256) mod_gemv_kernel(const float* __restrict__ tsilu,
                                                        const float* __restrict__ wmod,
                                                        const float* __restrict__ bmod, float* __restrict__ mod,
                                                        int B, int Nmod) {
     __shared__ float ts[MOD_BCHUNK][kTimeDim];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int n = blockIdx.x * 8 + warp;
-    float w[8];
-    if (n < Nmod) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) w[i] = __ldg(wmod + (size_t)n * kTimeDim + lane + 32 * i);
-    }
+    const int n0 = blockIdx.x * MOD_COLS + warp * (MOD_COLS / 8);
     for (int b0 = 0; b0 < B; b0 += MOD_BCHUNK) {
         const int nb = min(MOD_BCHUNK, B - b0);
         __syncthreads();
         for (int i = tid; i < nb * kTimeDim; i += 256) ts[i / kTimeDim][i % kTimeDim] = tsilu[(size_t)b0 * kTimeDim + i];
         __syncthreads();
-        if (n < Nmod) {
+#pragma unroll 2
+        for (int c = 0; c < MOD_COLS / 8; ++c) {
+            const int n = n0 + c;
+            if (n >= Nmod) break;
+            float w[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) w[i] = __ldg(wmod + (size_t)n * kTimeDim + lane + 32 * i);
+            const float bias = bmod[n];
             for (int bb = 0; bb < nb; ++bb) {
                 float acc = 0.f;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) acc = fmaf(ts[bb][lane + 32 * i], w[i], acc);
                 acc = warp_sum(acc);
-                if (lane == 0) mod[(size_t)(b0 + bb) * Nmod + n] = acc + bmod[n];
+                if (lane == 0) mod[(size_t)(b0 + bb) * Nmod + n] = acc + bias;
             }
         }
     }
@@ -266,17 +283,18 @@ inline int grid_for(size_t n, int block = 256, int cap = 148 * 16) {
 }  // namespace
 
 cudaError_t launch_time_embed(const float* t_hat, const float* freq, const float* w1, const float* b1,
-                              const float* w2, const float* b2, float sigma_data, float* tsilu, float* coef,
-                              int B, cudaStream_t st) {
-    if (B <= 0) return cudaErrorInvalidValue;
-    time_embed_kernel<<<B, 256, 0, st>>>(t_hat, freq, w1, b1, w2, b2, sigma_data, tsilu, coef);
+                              const float* w2, const float* b2, float sigma_data, float* tsilu, __half* ts_h,
+                              __half* ts_l, int rows_padded, float* coef, int B, cudaStream_t st) {
+    if (B <= 0 || (ts_h != nullptr && rows_padded < B)) return cudaErrorInvalidValue;
+    time_embed_kernel<<<ts_h != nullptr ? rows_padded : B, 256, 0, st>>>(t_hat, freq, w1, b1, w2, b2, sigma_data, tsilu, ts_h,
+                                                                       ts_l, coef, B);
     return cudaGetLastError();
 }
 
 cudaError_t launch_mod_gemv(const float* tsilu, const float* wmod, const float* bmod, float* mod, int B,
                             int Nmod, cudaStream_t st) {
     if (B <= 0 || Nmod <= 0) return cudaErrorInvalidValue;
-    mod_gemv_kernel<<<(Nmod + 7) / 8, 256, 0, st>>>(tsilu, wmod, bmod, mod, B, Nmod);
+    mod_gemv_kernel<<<(Nmod + MOD_COLS - 1) / MOD_COLS, 256, 0, st>>>(tsilu, wmod, bmod, mod, B, Nmod);
     return cudaGetLastError();
 }
 

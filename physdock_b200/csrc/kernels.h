@@ -55,10 +55,11 @@ cudaError_t launch_pair_bias(const float* pair, const float* mask, const float* 
                              cudaStream_t st);
 
 // ----------------------------------------------------------------------------- conditioning / glue
-// t_hat[B] -> tsilu[B,256] = SiLU(time_embedder(t_hat * c_noise)), coef[B,4] = (c_in, c_skip, c_out, t_hat)
+// t_hat[B] -> SiLU(time_embedder(t_hat * c_noise)) as fp32 tsilu[B,256] (optional) and/or as split planes
+// ts_h/ts_l [rows_padded,256] (rows >= B zeroed: the A operand of the modulation GEMM); coef[B,4] = (c_in, c_skip, c_out, t_hat)
 cudaError_t launch_time_embed(const float* t_hat, const float* freq, const float* w1, const float* b1,
-                              const float* w2, const float* b2, float sigma_data, float* tsilu, float* coef,
-                              int B, cudaStream_t st);
+                              const float* w2, const float* b2, float sigma_data, float* tsilu, __half* ts_h,
+                              __half* ts_l, int rows_padded, float* coef, int B, cudaStream_t st);
 // mod[B,Nmod] = tsilu[B,256] * wmod[Nmod,256]^T + bmod   (all AdaLN-Zero linears of the model at once)
 cudaError_t launch_mod_gemv(const float* tsilu, const float* wmod, const float* bmod, float* mod, int B,
                             int Nmod, cudaStream_t st);

@@ -146,6 +146,7 @@ class B200DiT(nn.Module):
                 offs[(stack, i, sub)] = off
                 off += 3 * c
         P["wmod"], P["bmod"] = torch.cat(mods_w, 0).contiguous(), torch.cat(mods_b, 0).contiguous()
+        P["wmod_h"], P["wmod_l"] = _split_planes(P["wmod"])     # the 36 modulations run as one tensor-core GEMM
         n_mod = off
         P["wx"], P["bx"] = sd["linear_x.weight"].contiguous(), sd["linear_x.bias"].contiguous()
         P["wdown_h"], P["wdown_l"] = _split_planes(sd["linear_downscale.weight"])
