@@ -141,6 +141,21 @@ def run_reference(args, rank):
     }))
 
 
+def attention_dram_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the attention kernel, from the committed
+    `ncu --set full` capture summarised in profiles/r01_attention_umma_ncu.txt (same shape as the bench)."""
+    p = os.path.join(ROOT, "profiles", "r01_attention_umma_ncu.txt")
+    try:
+        tot = 0.0
+        for line in open(p):
+            f = line.split()
+            if f and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                tot += float(f[1]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[f[2]]
+        return tot or None
+    except (OSError, ValueError, KeyError, IndexError):
+        return None
+
+
 def time_attention_kernel(dit, B, iters=12):
     """Average duration of the dominant kernel (atom pair-bias attention) measured with CUDA events on the
     launching stream; the 6 cached bias blocks (67 MB each) are cycled so no launch finds its bias in L2."""
@@ -284,9 +299,10 @@ def main():
                 "d2h_bytes_per_step": B * NA * 3 * 4, "ms_per_step": ms_e2e / K},
         "gpu_launches": K * launches_per_step,
         "clocks": clk,
-        "roofline": {"kernel": "attention_kernel (atom pair-bias attention, S=2048 H=4 D=32)", "bound": "tensor",
+        "roofline": {"kernel": "attention_umma_kernel (atom pair-bias attention, S=2048 H=4 D=32)", "bound": "tensor",
                      "achieved": f_attn / t_attn / 1e12, "peak": peaks["tf_burst"], "unit": "TFLOP/s",
-                     "frac": f_attn / t_attn / 1e12 / peaks["tf_burst"], "traffic": None,
+                     "frac": f_attn / t_attn / 1e12 / peaks["tf_burst"], "traffic": attention_dram_traffic(),
+                     "issued_mma_tflops": 3 * f_attn / t_attn / 1e12,
                      "peak_source": peaks["source"] + ", burst bf16", "launch_ms": t_attn * 1e3,
                      "algorithmic_gflop_per_launch": f_attn / 1e9},
     }
