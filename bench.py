@@ -133,7 +133,7 @@ def run_reference(args, rank):
     rate, sec = cpu_oracle_rate(n, B_cpu, threads)
     sample = f"{n} timed steps (+1 warm-up) of B={B_cpu} samples at Nt={NT}/Na={NA}, fp32 PyTorch CPU, {threads} threads"
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": 0, "steps": n,
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": n,
         "warmup": 1, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "Nt": NT, "Na": NA, "B": B_cpu},
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
@@ -187,6 +187,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--samples", type=int, default=B_PER_GPU, help="samples per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--physics", action="store_true",
+                    help="BASELINE.json configs[2]-style step: RDKit-free physics guidance on (40 synthetic conformer "
+                         "templates, template selection + weighted Kabsch projection every guided step)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -212,10 +215,16 @@ def main():
     dit = B200DiT.from_state_dict(make_dit_state(dims, seed=0), dims, device=dev)
     cx = {k: v.to(dev) for k, v in make_complex(NT, NA, dims, seed=1).items()}
     torch.manual_seed(123 + rank)                       # per-rank sampler seed
+    phys = {}
+    if args.physics:
+        from physdock_b200.synthetic import make_templates
+        phys = dict(align_ref_pos=True, ref_mol_poses=make_templates(cx, 40), mmff_gamma_0_factor=6.0)
+    else:
+        phys = dict(align_ref_pos=False)
     smp = DiffusionSampler(dit, cx, cx["a"], cx["ap"], cx["s"], cx["z"], num_sample=B, steps=SCHED_STEPS,
-                           karras_noise_schedule_power=RHO, align_ref_pos=False)
+                           karras_noise_schedule_power=RHO, **phys)
     smp.begin()
-    launches_per_step = dit.launches_per_denoise() + 2   # + centre_augment + euler
+    launches_per_step = dit.launches_per_denoise() + 2 + (3 if args.physics else 0)   # + centre_augment + euler (+ physics)
 
     def barrier():
         if world > 1:
@@ -289,7 +298,8 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "Nt": NT, "Na": NA, "samples_per_gpu": B, "schedule": "40 steps rho=1000",
+        "config": {"workload": WORKLOAD + (" + physics guidance (40 templates, Kabsch projection)" if args.physics else ""),
+                   "Nt": NT, "Na": NA, "samples_per_gpu": B, "schedule": "40 steps rho=1000",
                    "l2": "inputs larger than L2: 453 MB pair-bias cache + 203 MB weights streamed every step",
                    "batch_steps_per_s": world * K / (ms_total * 1e-3), "gather_final_coords_ms": ms_gather,
                    "gflop_per_sample_step": F / 1e9,

@@ -36,6 +36,9 @@ constexpr int NTHREADS = 320;
 constexpr int EPI_THREADS = 256;
 constexpr uint32_t TMEM_COLS = ACC * BN;
 
+// Debug-only compile switches used by tools/gemm_variants.sh to attribute time (never defined in the product build):
+//   PDK_DBG_NO_STORE  epilogue skips its global stores      PDK_DBG_NO_TMAWAIT  MMA warp does not wait for TMA data
+//   PDK_DBG_NO_EPI    epilogue only drains TMEM (no math, no stores)
 PDK_DEV void store8(float* dst, const float (&v)[32]) {
 #pragma unroll
     for (int i = 0; i < 8; ++i)
@@ -112,7 +115,9 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant_
             tc_fence_after();
             const uint32_t d = tmem + buf * BN;
             for (int kt = 0; kt < KT; ++kt) {
+#ifndef PDK_DBG_NO_TMAWAIT
                 mbar_wait(full(s), ph);
+#endif
                 tc_fence_after();
                 if (elect_one()) {
                     const uint32_t src = ring + s * STAGE_BYTES;
@@ -155,6 +160,10 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant_
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
                 const int col = n0 + ch * 32;
+#ifdef PDK_DBG_NO_EPI
+                if (v[0] == 123.456f && col == -1) p.out[row] = v[1];
+                continue;
+#endif
                 if constexpr (EPI == EPI_STORE) {
                     if (p.bias) {
 #pragma unroll
@@ -189,8 +198,14 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant_
                         split2(silu_fast(v[2 * i]) * v[16 + 2 * i], silu_fast(v[2 * i + 1]) * v[16 + 2 * i + 1], hi[i], lo[i]);
                     uint4* dh = reinterpret_cast<uint4*>(p.ph + (size_t)row * p.ldp + j0);
                     uint4* dl = reinterpret_cast<uint4*>(p.pl + (size_t)row * p.ldp + j0);
+#ifdef PDK_DBG_NO_STORE
+                    if (hi[0] == 0x12345678u && lo[7] == 0x9abcdef0u) {
+#endif
                     dh[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]); dh[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
                     dl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]); dl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+#ifdef PDK_DBG_NO_STORE
+                    }
+#endif
                 } else {   // EPI_QKV: this chunk is one head of q, k or v
                     const int which = col / p.c;
                     const int head = (col % p.c) / kHeadDim;

@@ -122,3 +122,16 @@ def test_physdock_module_surface(dit):
     from physdock_b200._lib import PdkError
     with pytest.raises(PdkError):
         model.sample_diffusion(cx, num_sample=2, steps=4, ref_mol=object())    # MMFF needs rdkit: loud, not silent
+
+
+def test_sharded_sampler_single_rank_equals_plain(dit):
+    """world_size 1: sample_diffusion_sharded(exact=True) consumes the generator like the plain sampler."""
+    from physdock_b200 import sampler as S
+    from physdock_b200.sharding import sample_diffusion_sharded
+    cx = to_dev(complex_64_512())
+    torch.manual_seed(11)
+    a = S.sample_diffusion(dit, cx, cx["a"], cx["ap"], cx["s"], cx["z"], num_sample=3, steps=5,
+                           karras_noise_schedule_power=1000, align_ref_pos=False)
+    b = sample_diffusion_sharded(dit, cx, cx["a"], cx["ap"], cx["s"], cx["z"], num_sample=3, seed=11, steps=5,
+                                 karras_noise_schedule_power=1000, align_ref_pos=False)
+    assert torch.equal(a, b)
