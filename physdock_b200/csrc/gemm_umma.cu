@@ -31,7 +31,12 @@ namespace {
 constexpr int BM = 128, BN = 128, BK = 64, STAGES = 3, ACC = 2;
 constexpr int TILE_BYTES = 128 * BK * 2;            // 16 KB: one fp16 plane tile, 128-byte rows (SWIZZLE_128B)
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;         // A_hi, A_lo, W_hi, W_lo
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;   // + slack to 1024-align the ring
+// Epilogue staging: a thread owns one output ROW, so storing straight from registers makes every store instruction
+// scatter 16 bytes to 32 different rows (measured: 14 of 36 us on the atom SwiGLU GEMM).  Each epilogue warp therefore
+// parks 16 words per row in a private padded smem tile (80-byte rows: conflict-free 128-bit writes and reads) and
+// writes it out row-contiguously, 8 rows x 64 bytes per instruction.
+constexpr int STG_ROW_BYTES = 80, STG_WARP_BYTES = 32 * STG_ROW_BYTES;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 8 * STG_WARP_BYTES + 1024;   // + slack to 1024-align the ring
 constexpr int NTHREADS = 320;
 constexpr int EPI_THREADS = 256;
 constexpr uint32_t TMEM_COLS = ACC * BN;
@@ -39,11 +44,6 @@ constexpr uint32_t TMEM_COLS = ACC * BN;
 // Debug-only compile switches used by tools/gemm_variants.sh to attribute time (never defined in the product build):
 //   PDK_DBG_NO_STORE  epilogue skips its global stores      PDK_DBG_NO_TMAWAIT  MMA warp does not wait for TMA data
 //   PDK_DBG_NO_EPI    epilogue only drains TMEM (no math, no stores)
-PDK_DEV void store8(float* dst, const float (&v)[32]) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-        reinterpret_cast<float4*>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-}
 // x * sigmoid(x) with MUFU ex2 / rcp (relative error ~3e-7; the IEEE expf + divide version cost ~50 instructions
 // per value and made the SwiGLU epilogue the bottleneck of the K=128 GEMMs)
 PDK_DEV float silu_fast(float x) {
@@ -143,14 +143,33 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant_
         const int ew = warp - 2;
         const int q = warp & 3;                       // TMEM lane quarter this warp may access
         const int chunk0 = (ew >> 2) * 2;             // warps 2-5: chunks 0,1; warps 6-9: chunks 2,3
+        const uint32_t stg = ring + STAGES * STAGE_BYTES + ew * STG_WARP_BYTES;
+        const int rr = lane >> 2, rc = lane & 3;      // write-out role: row (within a group of 8) and 16-byte chunk
+        // park 16 words of this thread's row, then hand each lane 4 consecutive words of row (it*8 + rr)
+        auto stage16 = [&](const uint32_t (&w)[16]) {
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(stg + lane * STG_ROW_BYTES + i * 16), "r"(w[4 * i]),
+                             "r"(w[4 * i + 1]), "r"(w[4 * i + 2]), "r"(w[4 * i + 3]) : "memory");
+            __syncwarp();
+        };
+        auto unstage = [&](int it) {
+            uint4 v;
+            asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                         : "r"(stg + (it * 8 + rr) * STG_ROW_BYTES + rc * 16));
+            return v;
+        };
         int lt = 0;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++lt) {
             const int buf = lt & 1;
             const int m0 = (t / num_n) * BM, n0 = (t % num_n) * BN;
             mbar_wait(tfull(buf), ((uint32_t)lt >> 1) & 1u);
             tc_fence_after();
-            const int row = m0 + q * 32 + lane;
+            const int row0 = m0 + q * 32;             // first row of this warp; this thread computes row0 + lane
             const uint32_t taddr = tmem + buf * BN + ((uint32_t)(q * 32) << 16);
+            // a 128-row tile never straddles samples (rows_per_sample % 128 == 0)
+            const int sample = (EPI == EPI_GATE_RESID || EPI == EPI_QKV) ? m0 / p.rows_per_sample : 0;
 #pragma unroll 1
             for (int ch = chunk0; ch < chunk0 + 2; ++ch) {
                 uint32_t raw[32];
@@ -161,49 +180,62 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant_
                 for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
                 const int col = n0 + ch * 32;
 #ifdef PDK_DBG_NO_EPI
-                if (v[0] == 123.456f && col == -1) p.out[row] = v[1];
+                if (v[0] == 123.456f && col == -1) p.out[row0] = v[1];
                 continue;
 #endif
-                if constexpr (EPI == EPI_STORE) {
+                if constexpr (EPI == EPI_STORE || EPI == EPI_GATE_RESID) {
                     if (p.bias) {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] += __ldg(p.bias + col + i);
+                        for (int i = 0; i < 8; ++i) {
+                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col) + i);
+                            v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
+                        }
                     }
-                    if (p.act_silu) {
+                    if constexpr (EPI == EPI_STORE) {
+                        if (p.act_silu) {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = silu_fast(v[i]);
+                            for (int i = 0; i < 32; ++i) v[i] = silu_fast(v[i]);
+                        }
+                    } else {
+                        const float* gate = p.gate + (size_t)sample * p.gate_stride + col;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float4 g4 = __ldg(reinterpret_cast<const float4*>(gate) + i);
+                            v[4 * i] *= g4.x; v[4 * i + 1] *= g4.y; v[4 * i + 2] *= g4.z; v[4 * i + 3] *= g4.w;
+                        }
                     }
-                    store8(p.out + (size_t)row * p.ldo + col, v);
-                } else if constexpr (EPI == EPI_GATE_RESID) {
-                    const float* gate = p.gate + (size_t)(row / p.rows_per_sample) * p.gate_stride + col;
-                    float* x = p.out + (size_t)row * p.ldo + col;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        float4 xv = reinterpret_cast<float4*>(x)[i];
-                        const float4 gv = __ldg(reinterpret_cast<const float4*>(gate) + i);
-                        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + col) + i);
-                        xv.x += (v[4 * i] + bv.x) * gv.x;
-                        xv.y += (v[4 * i + 1] + bv.y) * gv.y;
-                        xv.z += (v[4 * i + 2] + bv.z) * gv.z;
-                        xv.w += (v[4 * i + 3] + bv.w) * gv.w;
-                        reinterpret_cast<float4*>(x)[i] = xv;
+                    for (int half = 0; half < 2; ++half) {
+                        uint32_t w[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) w[i] = __float_as_uint(v[half * 16 + i]);
+                        stage16(w);
+#pragma unroll
+                        for (int it = 0; it < 4; ++it) {
+                            const uint4 u = unstage(it);
+                            float4* dst = reinterpret_cast<float4*>(p.out + (size_t)(row0 + it * 8 + rr) * p.ldo + col + half * 16 + rc * 4);
+                            float4 o = make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w));
+                            if constexpr (EPI == EPI_GATE_RESID) {
+                                const float4 x = *dst;
+                                o.x += x.x; o.y += x.y; o.z += x.z; o.w += x.w;
+                            }
+                            *dst = o;
+                        }
                     }
                 } else if constexpr (EPI == EPI_SWIGLU) {
                     // W rows interleaved in blocks of 16: columns [0,16) = w1 rows, [16,32) = w3 rows of hidden j0..j0+15
                     const int j0 = col / 2;
-                    uint32_t hi[8], lo[8];
+                    uint32_t w[16];     // words 0-7: hi halves of the 16 hidden values, 8-15: lo halves
 #pragma unroll
                     for (int i = 0; i < 8; ++i)
-                        split2(silu_fast(v[2 * i]) * v[16 + 2 * i], silu_fast(v[2 * i + 1]) * v[16 + 2 * i + 1], hi[i], lo[i]);
-                    uint4* dh = reinterpret_cast<uint4*>(p.ph + (size_t)row * p.ldp + j0);
-                    uint4* dl = reinterpret_cast<uint4*>(p.pl + (size_t)row * p.ldp + j0);
-#ifdef PDK_DBG_NO_STORE
-                    if (hi[0] == 0x12345678u && lo[7] == 0x9abcdef0u) {
-#endif
-                    dh[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]); dh[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-                    dl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]); dl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
-#ifdef PDK_DBG_NO_STORE
+                        split2(silu_fast(v[2 * i]) * v[16 + 2 * i], silu_fast(v[2 * i + 1]) * v[16 + 2 * i + 1], w[i], w[8 + i]);
+                    stage16(w);
+#ifndef PDK_DBG_NO_STORE
+#pragma unroll
+                    for (int it = 0; it < 4; ++it) {
+                        const uint4 u = unstage(it);
+                        __half* plane = (rc < 2) ? p.ph : p.pl;
+                        *reinterpret_cast<uint4*>(plane + (size_t)(row0 + it * 8 + rr) * p.ldp + j0 + (rc & 1) * 8) = u;
                     }
 #endif
                 } else {   // EPI_QKV: this chunk is one head of q, k or v
@@ -217,19 +249,24 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant_
                         const float inv = (1.0f / sqrtf(ss * (1.0f / kHeadDim) + p.rms_eps)) * (which == 0 ? p.q_scale : 1.0f);
                         const float* gain = which == 0 ? p.norm_q : p.norm_k;
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = v[i] * inv * __ldg(gain + i);
+                        for (int i = 0; i < 8; ++i) {
+                            const float4 g4 = __ldg(reinterpret_cast<const float4*>(gain) + i);
+                            v[4 * i] *= inv * g4.x; v[4 * i + 1] *= inv * g4.y; v[4 * i + 2] *= inv * g4.z; v[4 * i + 3] *= inv * g4.w;
+                        }
                     }
-                    __half* dh = which == 0 ? p.q : (which == 1 ? p.k : p.v);      // row = [hi 32 | lo 32] halves
-                    __half* dl = dh + kHeadDim;
-                    const size_t d0 = ((size_t)((row / p.rows_per_sample) * H + head) * p.rows_per_sample +
-                                       (row % p.rows_per_sample)) * (2 * kHeadDim);
+                    __half* dbase = which == 0 ? p.q : (which == 1 ? p.k : p.v);      // row = [hi 32 | lo 32] halves = 128 bytes
+                    const size_t tile_row = (size_t)(sample * H + head) * p.rows_per_sample + (row0 % p.rows_per_sample);
                     uint32_t hi[16], lo[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) split2(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        reinterpret_cast<uint4*>(dh + d0)[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
-                        reinterpret_cast<uint4*>(dl + d0)[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+                    for (int half = 0; half < 2; ++half) {
+                        stage16(half == 0 ? hi : lo);
+#pragma unroll
+                        for (int it = 0; it < 4; ++it) {
+                            const uint4 u = unstage(it);
+                            *reinterpret_cast<uint4*>(dbase + (tile_row + it * 8 + rr) * (2 * kHeadDim) + half * kHeadDim + rc * 8) = u;
+                        }
                     }
                 }
             }
@@ -272,6 +309,8 @@ cudaError_t launch_one(const GemmArgs& a, cudaStream_t st) {
 cudaError_t launch_gemm(GemmEpilogue epi, const GemmArgs& a, cudaStream_t st) {
     if (a.M <= 0 || a.N <= 0 || a.K <= 0 || a.M % BM || a.N % BN || a.K % BK) return cudaErrorInvalidValue;
     if (a.lda % 8 || a.ldw % 8) return cudaErrorInvalidValue;   // 16-byte global strides for TMA
+    if ((epi == EPI_GATE_RESID || epi == EPI_QKV) && (a.rows_per_sample <= 0 || a.rows_per_sample % BM))
+        return cudaErrorInvalidValue;                            // a row tile must not straddle samples
     switch (epi) {
         case EPI_STORE: return launch_one<EPI_STORE>(a, st);
         case EPI_GATE_RESID: return launch_one<EPI_GATE_RESID>(a, st);
