@@ -132,11 +132,13 @@ attention_umma_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_const
         }
         mbar_fence_init();
     }
+    griddep_launch();                 // PDL (see common.cuh)
     if (warp == 9) tmem_alloc(smem_u32(&tmem_slot), TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
+    griddep_wait();
 
     if (warp == 8) {
         // ================================================================= TMA producer
@@ -390,7 +392,7 @@ cudaError_t launch_attention(const AttnArgs& a_in, cudaStream_t st) {
     if ((e = get_tensor_map_f16(a.v, rows, 2 * D, 2 * D, BKV, 2 * D, 128, &mV)) != cudaSuccess) return e;
     if ((e = get_tensor_map_f32(a.bias, (uint64_t)a.H * a.S_pad, a.S_pad, a.S_pad, BQ, 32, 128, &mBias)) != cudaSuccess) return e;
     dim3 grid((a.B + G - 1) / G, a.S_pad / BQ, a.H);
-    attention_umma_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(mQ, mK, mV, mBias, a);
+    PDK_LAUNCH_CHECK(launch_pdl(attention_umma_kernel, grid, dim3(NTHREADS), (size_t)SMEM_BYTES, st, mQ, mK, mV, mBias, a));
     return cudaGetLastError();
 }
 

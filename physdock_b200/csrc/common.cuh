@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #define PDK_DEV __device__ __forceinline__
 
@@ -12,6 +13,14 @@ constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kPadBias = -1.0e30f;     // bias of padded key columns: exp2(kPadBias - m) == 0, stays finite
 constexpr int   kHeadDim = 32;           // attentions.py:223 (c_hidden)
 constexpr int   kTimeDim = 256;          // timestep_embeddings.py:157
+
+// ---- Programmatic Dependent Launch ---------------------------------------------------------------------------
+// Every kernel of the sampling step is launched with cudaLaunchAttributeProgrammaticStreamSerialization: it calls
+// griddep_launch() at entry (the next kernel in the stream may be scheduled as soon as all CTAs of this grid have
+// started) and griddep_wait() before it reads anything a predecessor wrote (returns when the preceding grid has
+// completed and flushed).  Launch latency and kernel prologues thus overlap the previous kernel's tail.
+PDK_DEV void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+PDK_DEV void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 PDK_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -83,6 +92,26 @@ PDK_DEV double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
+}
+
+
+#define PDK_LAUNCH_CHECK(expr)                 \
+    do {                                       \
+        cudaError_t e_ = (expr);               \
+        if (e_ != cudaSuccess) return e_;      \
+    } while (0)
+
+// host side: <<<>>> with the PDL attribute
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    static const int pdl = getenv("PDK_NO_PDL") == nullptr;     // measurement switch; PDL is on in production
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
 }  // namespace pdk

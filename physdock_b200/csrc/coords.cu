@@ -49,6 +49,8 @@ __global__ void __launch_bounds__(256) centre_augment_kernel(const float* __rest
                                                              const float* __restrict__ noise, float lambda,
                                                              float noise_scale, float trans_scale,
                                                              float* __restrict__ x_out, int Na) {
+    griddep_launch();
+    griddep_wait();
     __shared__ float scratch[8];
     __shared__ float sR[9];
     __shared__ float sMean[3];
@@ -102,6 +104,8 @@ __global__ void __launch_bounds__(256) euler_kernel(const float* __restrict__ x_
                                                     const float* __restrict__ aligned, const float* __restrict__ w,
                                                     const float* __restrict__ t_hat, float t_next, float eta,
                                                     float* __restrict__ x_next, int B, int Na) {
+    griddep_launch();
+    griddep_wait();
     const size_t total = (size_t)B * Na * 3;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const size_t r = i / 3;
@@ -123,6 +127,8 @@ __global__ void __launch_bounds__(256) euler_kernel(const float* __restrict__ x_
 __global__ void __launch_bounds__(128) template_eps_kernel(const float* __restrict__ x_den, const int* __restrict__ lig_idx,
                                                            const float* __restrict__ ref_dist, float* __restrict__ eps,
                                                            int Na, int n, int C) {
+    griddep_launch();
+    griddep_wait();
     extern __shared__ float sl[];     // [n][3]
     __shared__ float scratch[4];
     const int c = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
@@ -148,6 +154,8 @@ __global__ void __launch_bounds__(128) template_eps_kernel(const float* __restri
 __global__ void __launch_bounds__(128) template_pick_kernel(const float* __restrict__ eps, const float* __restrict__ ref_poses,
                                                             const int* __restrict__ lig_idx, int64_t* __restrict__ used,
                                                             float* __restrict__ batch_ref_pos, int Na, int n, int C) {
+    griddep_launch();
+    griddep_wait();
     __shared__ int best;
     const int b = blockIdx.x;
     if (threadIdx.x == 0) {
@@ -238,6 +246,8 @@ __device__ void kabsch3(const double H[3][3], double Q[3][3]) {
 __global__ void __launch_bounds__(256) rigid_align_kernel(const float* __restrict__ x_den, const float* __restrict__ x_exists,
                                                           const float* __restrict__ x_gt, int gt_batched,
                                                           const float* __restrict__ w, float* __restrict__ aligned, int Na) {
+    griddep_launch();
+    griddep_wait();
     __shared__ double scratch[8];
     __shared__ float sQ[9], sMuP[3], sMuG[3];
     const int b = blockIdx.x, tid = threadIdx.x;
@@ -297,7 +307,7 @@ cudaError_t launch_centre_augment(const float* x, const float* x_exists, const f
                                   const float* noise, float lambda, float noise_scale, float trans_scale,
                                   float* x_out, int B, int Na, cudaStream_t st) {
     if (B <= 0 || Na <= 0) return cudaErrorInvalidValue;
-    centre_augment_kernel<<<B, 256, 0, st>>>(x, x_exists, u4, trans, noise, lambda, noise_scale, trans_scale, x_out, Na);
+    PDK_LAUNCH_CHECK(launch_pdl(centre_augment_kernel, dim3(B), dim3(256), (size_t)(0), st, x, x_exists, u4, trans, noise, lambda, noise_scale, trans_scale, x_out, Na));
     return cudaGetLastError();
 }
 
@@ -305,28 +315,28 @@ cudaError_t launch_euler(const float* x_hat, const float* x_den, const float* al
                          const float* t_hat, float t_next, float eta, float* x_next, int B, int Na,
                          cudaStream_t st) {
     if (B <= 0 || Na <= 0 || (aligned != nullptr && w == nullptr)) return cudaErrorInvalidValue;
-    euler_kernel<<<grid_for((size_t)B * Na * 3), 256, 0, st>>>(x_hat, x_den, aligned, w, t_hat, t_next, eta, x_next, B, Na);
+    PDK_LAUNCH_CHECK(launch_pdl(euler_kernel, dim3(grid_for((size_t)B * Na * 3)), dim3(256), (size_t)(0), st, x_hat, x_den, aligned, w, t_hat, t_next, eta, x_next, B, Na));
     return cudaGetLastError();
 }
 
 cudaError_t launch_template_eps(const float* x_den, const int* lig_idx, const float* ref_dist, float* eps,
                                 int B, int Na, int n_lig, int C, cudaStream_t st) {
     if (B <= 0 || n_lig <= 0 || C <= 0 || (size_t)n_lig * 12 > 48 * 1024) return cudaErrorInvalidValue;
-    template_eps_kernel<<<dim3(C, B), 128, (size_t)n_lig * 3 * sizeof(float), st>>>(x_den, lig_idx, ref_dist, eps, Na, n_lig, C);
+    PDK_LAUNCH_CHECK(launch_pdl(template_eps_kernel, dim3(C, B), dim3(128), (size_t)n_lig * 3 * sizeof(float), st, x_den, lig_idx, ref_dist, eps, Na, n_lig, C));
     return cudaGetLastError();
 }
 
 cudaError_t launch_template_pick(const float* eps, const float* ref_poses, const int* lig_idx, int64_t* used,
                                  float* batch_ref_pos, int B, int Na, int n_lig, int C, cudaStream_t st) {
     if (B <= 0 || n_lig <= 0 || C <= 0) return cudaErrorInvalidValue;
-    template_pick_kernel<<<B, 128, 0, st>>>(eps, ref_poses, lig_idx, used, batch_ref_pos, Na, n_lig, C);
+    PDK_LAUNCH_CHECK(launch_pdl(template_pick_kernel, dim3(B), dim3(128), (size_t)(0), st, eps, ref_poses, lig_idx, used, batch_ref_pos, Na, n_lig, C));
     return cudaGetLastError();
 }
 
 cudaError_t launch_rigid_align(const float* x_den, const float* x_exists, const float* x_gt, int gt_batched,
                                const float* w, float* aligned, int B, int Na, cudaStream_t st) {
     if (B <= 0 || Na <= 0) return cudaErrorInvalidValue;
-    rigid_align_kernel<<<B, 256, 0, st>>>(x_den, x_exists, x_gt, gt_batched, w, aligned, Na);
+    PDK_LAUNCH_CHECK(launch_pdl(rigid_align_kernel, dim3(B), dim3(256), (size_t)(0), st, x_den, x_exists, x_gt, gt_batched, w, aligned, Na));
     return cudaGetLastError();
 }
 

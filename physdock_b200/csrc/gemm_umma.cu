@@ -78,11 +78,13 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant_
         mbar_fence_init();
         tma_prefetch_desc(&mAh); tma_prefetch_desc(&mAl); tma_prefetch_desc(&mWh); tma_prefetch_desc(&mWl);
     }
+    griddep_launch();                 // PDL: let the next kernel's launch + prologue overlap this kernel
     if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
+    griddep_wait();                   // everything above overlapped the previous kernel's tail; its outputs are visible now
 
     if (warp == 0) {
         // ================================================================= TMA producer
@@ -300,7 +302,8 @@ cudaError_t launch_one(const GemmArgs& a, cudaStream_t st) {
         if ((e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
     }
     const int tiles = (a.M / BM) * (a.N / BN);
-    gemm_umma_kernel<EPI><<<tiles < num_sms ? tiles : num_sms, NTHREADS, SMEM_BYTES, st>>>(mAh, mAl, mWh, mWl, a);
+    PDK_LAUNCH_CHECK(launch_pdl(gemm_umma_kernel<EPI>, dim3(tiles < num_sms ? tiles : num_sms), dim3(NTHREADS), (size_t)SMEM_BYTES, st,
+                                mAh, mAl, mWh, mWl, a));
     return cudaGetLastError();
 }
 

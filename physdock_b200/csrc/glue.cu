@@ -22,6 +22,8 @@ __global__ void __launch_bounds__(256) time_embed_kernel(const float* __restrict
                                                          float sigma_data, float* __restrict__ tsilu,
                                                          __half* __restrict__ ts_h, __half* __restrict__ ts_l,
                                                          float* __restrict__ coef, int B) {
+    griddep_launch();
+    griddep_wait();
     __shared__ __align__(16) float proj[kTimeDim];
     __shared__ __align__(16) float hid[kTimeDim];
     const int b = blockIdx.x, tid = threadIdx.x;
@@ -80,6 +82,8 @@ __global__ void __launch_bounds__(256) mod_gemv_kernel(const float* __restrict__
                                                        const float* __restrict__ wmod,
                                                        const float* __restrict__ bmod, float* __restrict__ mod,
                                                        int B, int Nmod) {
+    griddep_launch();
+    griddep_wait();
     __shared__ float ts[MOD_BCHUNK][kTimeDim];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n0 = blockIdx.x * MOD_COLS + warp * (MOD_COLS / 8);
@@ -114,6 +118,8 @@ template <int C>
 __global__ void __launch_bounds__(256) adaln_kernel(const float* __restrict__ x, const float* __restrict__ mod,
                                                     int mod_stride, int mod_off, __half* __restrict__ xh,
                                                     __half* __restrict__ xl, int rows, int S_pad, float eps) {
+    griddep_launch();
+    griddep_wait();
     constexpr int V = C / 128;     // float4 per lane
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -155,6 +161,8 @@ __global__ void __launch_bounds__(256) adaln_kernel(const float* __restrict__ x,
 
 __global__ void __launch_bounds__(256) split_kernel(const float* __restrict__ x, __half* __restrict__ xh,
                                                     __half* __restrict__ xl, size_t n4) {
+    griddep_launch();
+    griddep_wait();
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
         const float4 v = reinterpret_cast<const float4*>(x)[i];
         uint2 hi, lo;
@@ -170,6 +178,8 @@ __global__ void __launch_bounds__(256) precond_kernel(const float* __restrict__ 
                                                       const float* __restrict__ a, const float* __restrict__ wx,
                                                       const float* __restrict__ bx, float* __restrict__ ba, int B,
                                                       int Na, int S_pad, int c_a) {
+    griddep_launch();
+    griddep_wait();
     const int per_row = c_a / 4;
     const size_t total = (size_t)B * S_pad * per_row;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -199,6 +209,8 @@ __global__ void __launch_bounds__(256) precond_kernel(const float* __restrict__ 
 __global__ void __launch_bounds__(256) segment_mean_kernel(const float* __restrict__ h, const int* __restrict__ tok_start,
                                                            const float* __restrict__ s, float* __restrict__ bs, int B,
                                                            int Nt, int Sa_pad, int St_pad, int c_s) {
+    griddep_launch();
+    griddep_wait();
     const int per_row = c_s / 4;
     const size_t total = (size_t)B * St_pad * per_row;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -227,6 +239,8 @@ __global__ void __launch_bounds__(256) segment_mean_kernel(const float* __restri
 __global__ void __launch_bounds__(256) gather_add_kernel(float* __restrict__ ba, const float* __restrict__ up,
                                                          const int* __restrict__ atom2tok, int B, int Na, int Sa_pad,
                                                          int St_pad, int c_a) {
+    griddep_launch();
+    griddep_wait();
     const int per_row = c_a / 4;
     const size_t total = (size_t)B * Na * per_row;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -249,6 +263,8 @@ __global__ void __launch_bounds__(256) denoise_out_kernel(const float* __restric
                                                           const float* __restrict__ ln_b, const float* __restrict__ wr,
                                                           float* __restrict__ x_den, int B, int Na, int S_pad,
                                                           float eps) {
+    griddep_launch();
+    griddep_wait();
     const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (r >= B * Na) return;
@@ -286,15 +302,15 @@ cudaError_t launch_time_embed(const float* t_hat, const float* freq, const float
                               const float* w2, const float* b2, float sigma_data, float* tsilu, __half* ts_h,
                               __half* ts_l, int rows_padded, float* coef, int B, cudaStream_t st) {
     if (B <= 0 || (ts_h != nullptr && rows_padded < B)) return cudaErrorInvalidValue;
-    time_embed_kernel<<<ts_h != nullptr ? rows_padded : B, 256, 0, st>>>(t_hat, freq, w1, b1, w2, b2, sigma_data, tsilu, ts_h,
-                                                                       ts_l, coef, B);
+    PDK_LAUNCH_CHECK(launch_pdl(time_embed_kernel, dim3(ts_h != nullptr ? rows_padded : B), dim3(256), (size_t)(0), st, t_hat, freq, w1, b1, w2, b2, sigma_data, tsilu, ts_h,
+                                                                       ts_l, coef, B));
     return cudaGetLastError();
 }
 
 cudaError_t launch_mod_gemv(const float* tsilu, const float* wmod, const float* bmod, float* mod, int B,
                             int Nmod, cudaStream_t st) {
     if (B <= 0 || Nmod <= 0) return cudaErrorInvalidValue;
-    mod_gemv_kernel<<<(Nmod + MOD_COLS - 1) / MOD_COLS, 256, 0, st>>>(tsilu, wmod, bmod, mod, B, Nmod);
+    PDK_LAUNCH_CHECK(launch_pdl(mod_gemv_kernel, dim3((Nmod + MOD_COLS - 1) / MOD_COLS), dim3(256), (size_t)(0), st, tsilu, wmod, bmod, mod, B, Nmod));
     return cudaGetLastError();
 }
 
@@ -303,9 +319,9 @@ cudaError_t launch_adaln(const float* x, const float* mod, int mod_stride, int m
     const int rows = B * S_pad;
     if (rows <= 0 || (mod_off % 4) || (mod_stride % 4)) return cudaErrorInvalidValue;
     if (c == 128)
-        adaln_kernel<128><<<(rows + 7) / 8, 256, 0, st>>>(x, mod, mod_stride, mod_off, xh, xl, rows, S_pad, eps);
+        PDK_LAUNCH_CHECK(launch_pdl(adaln_kernel<128>, dim3((rows + 7) / 8), dim3(256), (size_t)(0), st, x, mod, mod_stride, mod_off, xh, xl, rows, S_pad, eps));
     else if (c == 512)
-        adaln_kernel<512><<<(rows + 7) / 8, 256, 0, st>>>(x, mod, mod_stride, mod_off, xh, xl, rows, S_pad, eps);
+        PDK_LAUNCH_CHECK(launch_pdl(adaln_kernel<512>, dim3((rows + 7) / 8), dim3(256), (size_t)(0), st, x, mod, mod_stride, mod_off, xh, xl, rows, S_pad, eps));
     else
         return cudaErrorInvalidValue;
     return cudaGetLastError();
@@ -313,29 +329,29 @@ cudaError_t launch_adaln(const float* x, const float* mod, int mod_stride, int m
 
 cudaError_t launch_split(const float* x, __half* xh, __half* xl, size_t n, cudaStream_t st) {
     if (n == 0 || n % 4) return cudaErrorInvalidValue;
-    split_kernel<<<grid_for(n / 4), 256, 0, st>>>(x, xh, xl, n / 4);
+    PDK_LAUNCH_CHECK(launch_pdl(split_kernel, dim3(grid_for(n / 4)), dim3(256), (size_t)(0), st, x, xh, xl, n / 4));
     return cudaGetLastError();
 }
 
 cudaError_t launch_precond(const float* x_hat, const float* coef, const float* a, const float* wx, const float* bx,
                            float* ba, int B, int Na, int S_pad, int c_a, cudaStream_t st) {
     if (c_a % 4 || Na > S_pad) return cudaErrorInvalidValue;
-    precond_kernel<<<grid_for((size_t)B * S_pad * (c_a / 4)), 256, 0, st>>>(x_hat, coef, a, wx, bx, ba, B, Na, S_pad, c_a);
+    PDK_LAUNCH_CHECK(launch_pdl(precond_kernel, dim3(grid_for((size_t)B * S_pad * (c_a / 4))), dim3(256), (size_t)(0), st, x_hat, coef, a, wx, bx, ba, B, Na, S_pad, c_a));
     return cudaGetLastError();
 }
 
 cudaError_t launch_segment_mean(const float* h, const int* tok_start, const float* s, float* bs, int B, int Nt,
                                 int Sa_pad, int St_pad, int c_s, cudaStream_t st) {
     if (c_s % 4 || Nt > St_pad) return cudaErrorInvalidValue;
-    segment_mean_kernel<<<grid_for((size_t)B * St_pad * (c_s / 4)), 256, 0, st>>>(h, tok_start, s, bs, B, Nt, Sa_pad,
-                                                                               St_pad, c_s);
+    PDK_LAUNCH_CHECK(launch_pdl(segment_mean_kernel, dim3(grid_for((size_t)B * St_pad * (c_s / 4))), dim3(256), (size_t)(0), st, h, tok_start, s, bs, B, Nt, Sa_pad,
+                                                                               St_pad, c_s));
     return cudaGetLastError();
 }
 
 cudaError_t launch_gather_add(float* ba, const float* up, const int* atom2tok, int B, int Na, int Sa_pad,
                               int St_pad, int c_a, cudaStream_t st) {
     if (c_a % 4) return cudaErrorInvalidValue;
-    gather_add_kernel<<<grid_for((size_t)B * Na * (c_a / 4)), 256, 0, st>>>(ba, up, atom2tok, B, Na, Sa_pad, St_pad, c_a);
+    PDK_LAUNCH_CHECK(launch_pdl(gather_add_kernel, dim3(grid_for((size_t)B * Na * (c_a / 4))), dim3(256), (size_t)(0), st, ba, up, atom2tok, B, Na, Sa_pad, St_pad, c_a));
     return cudaGetLastError();
 }
 
@@ -343,7 +359,7 @@ cudaError_t launch_denoise_out(const float* ba, const float* x_hat, const float*
                                const float* ln_b, const float* wr, float* x_den, int B, int Na, int S_pad,
                                int c_a, float eps, cudaStream_t st) {
     if (c_a != 128) return cudaErrorInvalidValue;
-    denoise_out_kernel<<<(B * Na + 7) / 8, 256, 0, st>>>(ba, x_hat, coef, ln_w, ln_b, wr, x_den, B, Na, S_pad, eps);
+    PDK_LAUNCH_CHECK(launch_pdl(denoise_out_kernel, dim3((B * Na + 7) / 8), dim3(256), (size_t)(0), st, ba, x_hat, coef, ln_w, ln_b, wr, x_den, B, Na, S_pad, eps));
     return cudaGetLastError();
 }
 

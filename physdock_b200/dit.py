@@ -66,6 +66,7 @@ class B200DiT(nn.Module):
         self._complex_sig = None
         self._complex_keep = None
         self._workspace: Optional[torch.Tensor] = None
+        self._graphs: Dict[tuple, object] = {}
         self._block_array = None
 
     # ------------------------------------------------------------------ construction helpers
@@ -224,6 +225,7 @@ class B200DiT(nn.Module):
         # the handle keeps raw pointers into these
         self._complex_keep = dict(a=a_, s=s_, tok_start=tok_start, atom2tok=atom2tok, bias_a=bias_a, bias_t=bias_t,
                                   Na=Na, Nt=Nt)
+        self._graphs.clear()
 
     @staticmethod
     def _complex_signature(batch, a, ap, s, z):
@@ -257,6 +259,30 @@ class B200DiT(nn.Module):
             out = torch.empty_like(x_hat)
         _lib.check(lib.pdk_dit_denoise(self._handle, _lib.ptr(x_hat), _lib.ptr(t_hat), B, _lib.ptr(ws), ws.numel(),
                                        _lib.ptr(out), _lib.stream_ptr(dev)), "pdk_dit_denoise")
+        return out
+
+    def denoise_graphed(self, x_hat: torch.Tensor, t_hat: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+        """`denoise` replayed from a CUDA graph (one graph per set of argument buffers and prepared complex).
+
+        The call enqueues ~136 kernels whose arguments are all pointers into persistent buffers, so the whole
+        denoiser is captured once and replayed with a single launch; x_hat / t_hat / out must be persistent
+        tensors that the caller updates in place (DiffusionSampler does)."""
+        if not (x_hat.is_contiguous() and t_hat.is_contiguous() and out.is_contiguous()
+                and x_hat.dtype == t_hat.dtype == out.dtype == torch.float32):
+            return self.denoise(x_hat, t_hat, out)
+        key = (x_hat.data_ptr(), t_hat.data_ptr(), out.data_ptr(), tuple(x_hat.shape), id(self._complex_keep),
+               self._pack_sig is not None and hash(self._pack_sig))
+        g = self._graphs.get(key)
+        if g is None:
+            self.denoise(x_hat, t_hat, out)          # warm-up: workspace, tensor maps, function attributes
+            torch.cuda.synchronize(x_hat.device)
+            if len(self._graphs) > 8:
+                self._graphs.clear()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.denoise(x_hat, t_hat, out)
+            self._graphs[key] = g
+        g.replay()
         return out
 
     def forward(self, batch: Dict[str, torch.Tensor], x_hat: torch.Tensor, t_hat: torch.Tensor, a: torch.Tensor,

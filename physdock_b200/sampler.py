@@ -15,6 +15,7 @@ on the same device type under the same `torch.manual_seed`.
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, Dict, List, Optional
 
 import torch
@@ -142,8 +143,10 @@ class DiffusionSampler:
                  step_scale_eta: float = 1.5, ode_step_scale_eta: float = 1.0, ref_mol=None,
                  ref_mol_poses: Optional[torch.Tensor] = None, use_ref_mol_poses: bool = False,
                  mmff_gamma_0_factor: float = 1.0, mmff_iters: int = 5, align_ref_pos: bool = True,
-                 karras_noise_schedule_power: float = 7, rng=None, mmff_fn: Optional[Callable] = None):
+                 karras_noise_schedule_power: float = 7, rng=None, mmff_fn: Optional[Callable] = None,
+                 use_cuda_graph: bool = True):
         dev = batch["x_gt"].device
+        self.use_cuda_graph = use_cuda_graph and os.environ.get("PDK_NO_GRAPH") is None
         if dev.type != "cuda":
             raise _lib.PdkError("sample_diffusion needs the batch on a CUDA device (no CPU fallback)")
         self.dit, self.dev, self.B, self.Na = dit, dev, num_sample, batch["x_gt"].shape[-2]
@@ -213,7 +216,10 @@ class DiffusionSampler:
         centre_augment_noise(self.x_next, self.x_exists, u4, trans, noise, self.lam, noise_scale, out=self.x_hat)
         if teacher_x_hat is not None:
             self.x_hat.copy_(teacher_x_hat)
-        self.dit.denoise(self.x_hat, self.t_hat_dev, out=self.x_den)
+        if self.use_cuda_graph:
+            self.dit.denoise_graphed(self.x_hat, self.t_hat_dev, self.x_den)
+        else:
+            self.dit.denoise(self.x_hat, self.t_hat_dev, out=self.x_den)
         self.last_used = None
         physics = False
         if self.align_ref_pos and bool(t_cur > self.gamma_min * self.mmff_factor):
