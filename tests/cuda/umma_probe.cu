@@ -629,6 +629,79 @@ __global__ void __launch_bounds__(128) probe_il_kernel(const __grid_constant__ C
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
 
+
+// ---- test 10: cta_group::2 pair GEMM.  Cluster of 2 CTAs computes D[256 x 128] = A[256 x K] B[128 x K]^T: each CTA holds its 128
+// rows of A and 64 of the 128 rows of B; the leader issues M=256 MMAs that read both CTAs' smem and write both CTAs' TMEM.
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum));
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128)
+probe_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, float* __restrict__ D, int kblocks) {
+    extern __shared__ __align__(1024) uint8_t smem_[];
+    __shared__ __align__(8) uint64_t bars[2];        // [0] full (used in the leader), [1] mma_done (arrives in both CTAs)
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const uint32_t rank = cluster_rank();
+    const uint32_t smem = (smem_u32(smem_) + 1023u) & ~1023u;
+    const uint32_t sA = smem, sB = smem + 16384;      // A: 128 rows x 128 B; B half: 64 rows x 128 B
+    const uint32_t bar_full = smem_u32(&bars[0]), bar_done = smem_u32(&bars[1]);
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(128));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+    }
+    if (tid == 0) { mbar_init(bar_full, 1); mbar_init(bar_done, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_base_s;
+    uint32_t phase = 0;
+    for (int kb = 0; kb < kblocks; ++kb) {
+        if (tid == 0) {
+            if (rank == 0) mbar_expect_tx(bar_full, 2 * (16384 + 8192));          // bytes landing in BOTH CTAs
+            tma_load_2d_2sm(sA, &mapA, bar_full, kb * 64, (int)rank * 128);      // my 128 rows of A
+            tma_load_2d_2sm(sB, &mapB, bar_full, kb * 64, (int)rank * 64);       // my 64 rows of B
+            if (rank == 0) {
+                mbar_wait(bar_full, phase);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t hb = ((1024u >> 4) & 0x3FFF) | (1u << 14) | (2u << 29);
+                const uint64_t da = ((uint64_t)hb << 32) | (1ull << 16) | (uint64_t)((sA >> 4) & 0x3FFF);
+                const uint64_t db = ((uint64_t)hb << 32) | (1ull << 16) | (uint64_t)((sB >> 4) & 0x3FFF);
+                const uint32_t idesc = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+                for (int k = 0; k < 4; ++k) umma_f16_2sm(tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                umma_commit_2sm(bar_done, 3);
+            }
+        }
+        mbar_wait(bar_done, phase);       // both CTAs: the MMAs have finished reading this stage's smem
+        phase ^= 1;
+        __syncthreads();
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    for (int c0 = 0; c0 < 128; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32p(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        for (int i = 0; i < 32; ++i) D[(size_t)(rank * 128 + tid) * 128 + c0 + i] = __uint_as_float(v[i]);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128));
+}
+
 static uint32_t desc_hi(uint32_t sbo_bytes, uint32_t layout_type) {
     return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | (layout_type << 29);   // SBO | version=1 (bit 46) | layout (bits 61..63)
 }
@@ -674,6 +747,42 @@ int main(int argc, char** argv) {
 
 
 
+
+    if (test == 10) {
+        const int M2 = 256, N2 = 128, K2 = 256;
+        std::vector<float> A2((size_t)M2 * K2), B2((size_t)N2 * K2);
+        srand(4242);
+        for (auto& v : A2) v = (rand() % 2001 - 1000) / 500.0f;
+        for (auto& v : B2) v = (rand() % 2001 - 1000) / 500.0f;
+        std::vector<__half> Ah2(A2.size()), Bh2(B2.size());
+        for (size_t i = 0; i < A2.size(); ++i) Ah2[i] = __float2half_rn(A2[i]);
+        for (size_t i = 0; i < B2.size(); ++i) Bh2[i] = __float2half_rn(B2[i]);
+        __half *dA2, *dB2; float* dD2;
+        CK(cudaMalloc(&dA2, A2.size() * 2)); CK(cudaMalloc(&dB2, B2.size() * 2)); CK(cudaMalloc(&dD2, (size_t)M2 * N2 * 4));
+        CK(cudaMemcpy(dA2, Ah2.data(), A2.size() * 2, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(dB2, Bh2.data(), B2.size() * 2, cudaMemcpyHostToDevice));
+        CK(cudaMemset(dD2, 0xFF, (size_t)M2 * N2 * 4));
+        CUtensorMap mA2 = make_map(enc, dA2, M2, K2, 128, 64, CU_TENSOR_MAP_SWIZZLE_128B);
+        CUtensorMap mB2 = make_map(enc, dB2, N2, K2, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B);
+        CK(cudaFuncSetAttribute(probe_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 24576 + 1024));
+        probe_pair_kernel<<<2, 128, 24576 + 1024>>>(mA2, mB2, dD2, K2 / 64);
+        CK(cudaGetLastError());
+        CK(cudaDeviceSynchronize());
+        std::vector<float> D2((size_t)M2 * N2);
+        CK(cudaMemcpy(D2.data(), dD2, D2.size() * 4, cudaMemcpyDeviceToHost));
+        double me = 0, mr = 0; int bi = -1, bj = -1;
+        for (int i = 0; i < M2; ++i)
+            for (int j = 0; j < N2; ++j) {
+                double ref = 0;
+                for (int k = 0; k < K2; ++k) ref += (double)__half2float(Ah2[(size_t)i * K2 + k]) * (double)__half2float(Bh2[(size_t)j * K2 + k]);
+                const double e = fabs(ref - (double)D2[(size_t)i * N2 + j]);
+                if (!(e <= me)) { me = e; bi = i; bj = j; }
+                mr = fmax(mr, fabs(ref));
+            }
+        const bool pass = me <= 1e-4 * mr + 1e-4;
+        printf("PROBE test=10 (cta_group::2 pair GEMM 256x128x256) max_err=%.3e at (%d,%d) max_ref=%.2f %s\n", me, bi, bj, mr, pass ? "PASS" : "FAIL");
+        return pass ? 0 : 1;
+    }
     if (test == 9) {
         std::vector<float> Q(128 * 32), K(128 * 32), V(128 * 32), Pm(128 * 128);
         srand(99);
