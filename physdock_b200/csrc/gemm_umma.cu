@@ -7,18 +7,20 @@
 // C[M,N] = A[M,K] W[N,K]^T with A, W stored as (hi, lo) fp16 planes; per K=16 slice three MMAs
 // (Al*Wh + Ah*Wl + Ah*Wh) accumulate in fp32 in TMEM.
 //
-// PERSISTENT kernel, 320 threads per CTA, warp-specialised.  Two tilings:
-//   PAIR (M % 256 == 0, the normal case): a CLUSTER OF TWO CTAs owns a 256 x 128 tile; each CTA loads its 128 rows of A
-//        and 64 of the 128 W rows, the leader issues tcgen05.mma.cta_group::2 (M = 256) into both CTAs' TMEM.  Per CTA a
-//        stage is 48 KB for 768 MMA cycles instead of 64 KB: the single-CTA tiling was bound by TMA ingest (~48 B/clk/SM
-//        against the 83 B/clk it needs, profiles/r01_gemm_umma_token_swiglu_ncu.txt).
-//   single CTA (fallback when M/128 is odd): 128 x 128 tiles.
+// PERSISTENT kernel, 576 threads per CTA, warp-specialised.  Two tilings:
+//   PAIR (M % 256 == 0 and K*N >= 700k, i.e. the token SwiGLU / w2 / QKV shapes): a CLUSTER OF TWO CTAs owns a 256 x 128
+//        tile; each CTA loads its 128 rows of A and 64 of the 128 W rows, the leader issues tcgen05.mma.cta_group::2
+//        (M = 256) into both CTAs' TMEM.  Per CTA a stage is 48 KB for 768 MMA cycles instead of 64 KB (the single-CTA
+//        tiling is bound by TMA ingest, ~48 B/clk/SM against the 83 B/clk it needs).  Measured (tools/time_gemm.py):
+//        token SwiGLU 28.9 -> 26.4 us, token w2 21.0 -> 19.7 us; the K = 128 atom shapes LOSE 1-6 us to the cluster
+//        launch / two-CTA handshakes, so they stay on the single-CTA tiling.
+//   single CTA: 128 x 128 tiles.
 // Tiles are walked n-fastest so concurrently running CTAs share the A tile in L2.  Roles:
 //   warp 0   : TMA producer: 4 plane tiles [128 rows x 64 halves] per stage, SWIZZLE_128B, 3-stage ring (192 KB)
 //              that runs ahead across tile boundaries
 //   warp 1   : TMEM allocator + MMA issuer: 12 x tcgen05.mma.kind::f16 M128 N128 K16 per stage into one of TWO
 //              128-column accumulators, so the epilogue of tile i overlaps the main loop of tile i+1
-//   warps 2-9: epilogue (two warps per TMEM lane quarter, two 32-column chunks each).  A THREAD owns one output
+//   warps 2-17: epilogue (four warps per TMEM lane quarter, one 32-column chunk each).  A THREAD owns one output
 //              row and reads 32 consecutive accumulator columns per tcgen05.ld -- exactly one attention head / one
 //              SwiGLU column block, so the per-head RMSNorm and the SwiGLU product need no cross-thread traffic.
 // (The first version launched one CTA per tile: tensor pipe 40% busy, the rest was per-tile prologue/epilogue and
@@ -38,12 +40,12 @@ constexpr int TILE_BYTES = 128 * BK * 2;            // 16 KB: one fp16 plane til
 constexpr int RING_BYTES = 192 * 1024;
 // Epilogue staging: a thread owns one output ROW, so storing straight from registers makes every store instruction
 // scatter 16 bytes to 32 different rows (measured: 14 of 36 us on the atom SwiGLU GEMM).  Each epilogue warp therefore
-// parks 16 words per row in a private padded smem tile (80-byte rows: conflict-free 128-bit writes and reads) and
-// writes it out row-contiguously, 8 rows x 64 bytes per instruction.
-constexpr int STG_ROW_BYTES = 80, STG_WARP_BYTES = 32 * STG_ROW_BYTES;
-constexpr int SMEM_BYTES = RING_BYTES + 8 * STG_WARP_BYTES + 1024;   // + slack to 1024-align the ring
-constexpr int NTHREADS = 320;
-constexpr int EPI_THREADS = 256;
+// parks 8 words per row in a private padded smem tile (48-byte rows: conflict-free 128-bit writes and reads) and
+// writes it out row-contiguously, 16 rows x 32 bytes per instruction.
+constexpr int EPI_WARPS = 16;
+constexpr int STG_ROW_BYTES = 48, STG_WARP_BYTES = 32 * STG_ROW_BYTES;
+constexpr int SMEM_BYTES = RING_BYTES + EPI_WARPS * STG_WARP_BYTES + 1024;   // + slack to 1024-align the ring
+constexpr int NTHREADS = (2 + EPI_WARPS) * 32;
 constexpr uint32_t TMEM_COLS = ACC * BN;
 
 // Debug-only compile switches used by tools/gemm_variants.sh to attribute time (never defined in the product build):
@@ -87,7 +89,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant_
 #pragma unroll
         for (int s = 0; s < STAGES; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
 #pragma unroll
-        for (int b = 0; b < ACC; ++b) { mbar_init(tfull(b), 1); mbar_init(tempty(b), PAIR ? 16 : 8); }   // one arrival per epilogue warp
+        for (int b = 0; b < ACC; ++b) { mbar_init(tfull(b), 1); mbar_init(tempty(b), PAIR ? 2 * EPI_WARPS : EPI_WARPS); }   // one arrival per epilogue warp
         mbar_fence_init();
         tma_prefetch_desc(&mAh); tma_prefetch_desc(&mAl); tma_prefetch_desc(&mWh); tma_prefetch_desc(&mWl);
     }
@@ -177,142 +179,152 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant_
             }
         }
     } else {
-        // ================================================================= epilogue: 8 warps, thread = (row, 2 chunks)
+        // ================================================================= epilogue: 16 warps, thread = (row, one 32-column chunk)
+        // Four warps per TMEM lane quarter, one chunk each.  With 8 warps x 2 chunks the epilogue was a serial latency
+        // chain per warp (tcgen05.ld -> math -> staging -> residual load -> store, twice) and cost 9-12 us on every atom
+        // GEMM whose main loop takes 5-10 us (tools/time_gemm.py with -DPDK_DBG_NO_EPI); the residual tile is now also
+        // fetched BEFORE the accumulator is complete.
         const int ew = warp - 2;
         const int q = warp & 3;                       // TMEM lane quarter this warp may access
-        const int chunk0 = (ew >> 2) * 2;             // warps 2-5: chunks 0,1; warps 6-9: chunks 2,3
+        const int ch = ew >> 2;                       // warps 2-5: chunk 0, 6-9: 1, 10-13: 2, 14-17: 3 (each group covers all quarters)
         const uint32_t stg = ring + STAGES * STAGE_BYTES + ew * STG_WARP_BYTES;
-        const int rr = lane >> 2, rc = lane & 3;      // write-out role: row (within a group of 8) and 16-byte chunk
-        // park 16 words of this thread's row, then hand each lane 4 consecutive words of row (it*8 + rr)
-        auto stage16 = [&](const uint32_t (&w)[16]) {
+        const int rr = lane >> 1, rc = lane & 1;      // write-out role: row (within a group of 16) and 16-byte piece
+        // park 8 words of this thread's row, then hand each lane 4 consecutive words of rows rr and 16 + rr
+        auto stage8 = [&](uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4, uint32_t w5, uint32_t w6, uint32_t w7) {
             __syncwarp();
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(stg + lane * STG_ROW_BYTES + i * 16), "r"(w[4 * i]),
-                             "r"(w[4 * i + 1]), "r"(w[4 * i + 2]), "r"(w[4 * i + 3]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(stg + lane * STG_ROW_BYTES), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(stg + lane * STG_ROW_BYTES + 16), "r"(w4), "r"(w5), "r"(w6), "r"(w7) : "memory");
             __syncwarp();
         };
         auto unstage = [&](int it) {
             uint4 v;
             asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                         : "r"(stg + (it * 8 + rr) * STG_ROW_BYTES + rc * 16));
+                         : "r"(stg + (it * 16 + rr) * STG_ROW_BYTES + rc * 16));
             return v;
         };
         int lt = 0;
         for (int t = worker; t < num_tiles; t += nworkers, ++lt) {
             const int buf = lt & 1;
             const int m0 = (t / num_n) * TILE_M + (int)rank * BM, n0 = (t % num_n) * BN;
-            mbar_wait(tfull(buf), ((uint32_t)lt >> 1) & 1u);
-            tc_fence_after();
             const int row0 = m0 + q * 32;             // first row of this warp; this thread computes row0 + lane
-            const uint32_t taddr = tmem + buf * BN + ((uint32_t)(q * 32) << 16);
+            const int col = n0 + ch * 32;
             // a 128-row tile never straddles samples (rows_per_sample % 128 == 0)
             const int sample = (EPI == EPI_GATE_RESID || EPI == EPI_QKV) ? m0 / p.rows_per_sample : 0;
-#pragma unroll 1
-            for (int ch = chunk0; ch < chunk0 + 2; ++ch) {
-                uint32_t raw[32];
-                tmem_ld32(taddr + ch * 32, raw);
-                tmem_ld_wait();
-                float v[32];
+            float4 xres[8];                           // EPI_GATE_RESID: the residual values this lane will update
+            if constexpr (EPI == EPI_GATE_RESID) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
-                const int col = n0 + ch * 32;
-#ifdef PDK_DBG_NO_EPI
-                if (v[0] == 123.456f && col == -1) p.out[row0] = v[1];
-                continue;
-#endif
-                if constexpr (EPI == EPI_STORE || EPI == EPI_GATE_RESID) {
-                    if (p.bias) {
+                for (int ps = 0; ps < 4; ++ps)
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col) + i);
-                            v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
-                        }
-                    }
-                    if constexpr (EPI == EPI_STORE) {
-                        if (p.act_silu) {
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) v[i] = silu_fast(v[i]);
-                        }
-                    } else {
-                        const float* gate = p.gate + (size_t)sample * p.gate_stride + col;
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const float4 g4 = __ldg(reinterpret_cast<const float4*>(gate) + i);
-                            v[4 * i] *= g4.x; v[4 * i + 1] *= g4.y; v[4 * i + 2] *= g4.z; v[4 * i + 3] *= g4.w;
-                        }
-                    }
-#pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-                        uint32_t w[16];
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) w[i] = __float_as_uint(v[half * 16 + i]);
-                        stage16(w);
-#pragma unroll
-                        for (int it = 0; it < 4; ++it) {
-                            const uint4 u = unstage(it);
-                            float4* dst = reinterpret_cast<float4*>(p.out + (size_t)(row0 + it * 8 + rr) * p.ldo + col + half * 16 + rc * 4);
-                            float4 o = make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w));
-                            if constexpr (EPI == EPI_GATE_RESID) {
-                                const float4 x = *dst;
-                                o.x += x.x; o.y += x.y; o.z += x.z; o.w += x.w;
-                            }
-                            *dst = o;
-                        }
-                    }
-                } else if constexpr (EPI == EPI_SWIGLU) {
-                    // W rows interleaved in blocks of 16: columns [0,16) = w1 rows, [16,32) = w3 rows of hidden j0..j0+15
-                    const int j0 = col / 2;
-                    uint32_t w[16];     // words 0-7: hi halves of the 16 hidden values, 8-15: lo halves
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        split2(silu_fast(v[2 * i]) * v[16 + 2 * i], silu_fast(v[2 * i + 1]) * v[16 + 2 * i + 1], w[i], w[8 + i]);
-                    stage16(w);
-#ifndef PDK_DBG_NO_STORE
-#pragma unroll
-                    for (int it = 0; it < 4; ++it) {
-                        const uint4 u = unstage(it);
-                        __half* plane = (rc < 2) ? p.ph : p.pl;
-                        *reinterpret_cast<uint4*>(plane + (size_t)(row0 + it * 8 + rr) * p.ldp + j0 + (rc & 1) * 8) = u;
-                    }
-#endif
-                } else {   // EPI_QKV: this chunk is one head of q, k or v
-                    const int which = col / p.c;
-                    const int head = (col % p.c) / kHeadDim;
-                    const int H = p.c / kHeadDim;
-                    if (which < 2) {    // per-head RMSNorm (rms_norm.py:14-19); q additionally carries log2e/sqrt(32)
-                        float ss = 0.f;
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) ss = fmaf(v[i], v[i], ss);
-                        const float inv = (1.0f / sqrtf(ss * (1.0f / kHeadDim) + p.rms_eps)) * (which == 0 ? p.q_scale : 1.0f);
-                        const float* gain = which == 0 ? p.norm_q : p.norm_k;
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const float4 g4 = __ldg(reinterpret_cast<const float4*>(gain) + i);
-                            v[4 * i] *= inv * g4.x; v[4 * i + 1] *= inv * g4.y; v[4 * i + 2] *= inv * g4.z; v[4 * i + 3] *= inv * g4.w;
-                        }
-                    }
-                    __half* dbase = which == 0 ? p.q : (which == 1 ? p.k : p.v);      // row = [hi 32 | lo 32] halves = 128 bytes
-                    const size_t tile_row = (size_t)(sample * H + head) * p.rows_per_sample + (row0 % p.rows_per_sample);
-                    uint32_t hi[16], lo[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) split2(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
-#pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-                        stage16(half == 0 ? hi : lo);
-#pragma unroll
-                        for (int it = 0; it < 4; ++it) {
-                            const uint4 u = unstage(it);
-                            *reinterpret_cast<uint4*>(dbase + (tile_row + it * 8 + rr) * (2 * kHeadDim) + half * kHeadDim + rc * 8) = u;
-                        }
-                    }
-                }
+                    for (int it = 0; it < 2; ++it)
+                        xres[ps * 2 + it] = *reinterpret_cast<const float4*>(p.out + (size_t)(row0 + it * 16 + rr) * p.ldo + col + ps * 8 + rc * 4);
             }
+            mbar_wait(tfull(buf), ((uint32_t)lt >> 1) & 1u);
+            tc_fence_after();
+            const uint32_t taddr = tmem + buf * BN + ((uint32_t)(q * 32) << 16);
+            uint32_t raw[32];
+            tmem_ld32(taddr + ch * 32, raw);
+            tmem_ld_wait();
+            // the accumulator chunk is in registers: release it to the MMA warp before the math / stores
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) {                          // this warp is done reading accumulator `buf`
+            if (lane == 0) {
                 if constexpr (PAIR) mbar_arrive_cluster(tempty(buf), 0);      // the leader's MMA warp waits for both CTAs
                 else mbar_arrive(tempty(buf));
+            }
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+#ifdef PDK_DBG_NO_EPI
+            if (v[0] == 123.456f && col == -1) p.out[row0] = v[1];
+            continue;
+#endif
+            if constexpr (EPI == EPI_STORE || EPI == EPI_GATE_RESID) {
+                if (p.bias) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col) + i);
+                        v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
+                    }
+                }
+                if constexpr (EPI == EPI_STORE) {
+                    if (p.act_silu) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = silu_fast(v[i]);
+                    }
+                } else {
+                    const float* gate = p.gate + (size_t)sample * p.gate_stride + col;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 g4 = __ldg(reinterpret_cast<const float4*>(gate) + i);
+                        v[4 * i] *= g4.x; v[4 * i + 1] *= g4.y; v[4 * i + 2] *= g4.z; v[4 * i + 3] *= g4.w;
+                    }
+                }
+#pragma unroll
+                for (int ps = 0; ps < 4; ++ps) {
+                    stage8(__float_as_uint(v[ps * 8]), __float_as_uint(v[ps * 8 + 1]), __float_as_uint(v[ps * 8 + 2]), __float_as_uint(v[ps * 8 + 3]),
+                           __float_as_uint(v[ps * 8 + 4]), __float_as_uint(v[ps * 8 + 5]), __float_as_uint(v[ps * 8 + 6]), __float_as_uint(v[ps * 8 + 7]));
+#pragma unroll
+                    for (int it = 0; it < 2; ++it) {
+                        const uint4 u = unstage(it);
+                        float4* dst = reinterpret_cast<float4*>(p.out + (size_t)(row0 + it * 16 + rr) * p.ldo + col + ps * 8 + rc * 4);
+                        float4 o = make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w));
+                        if constexpr (EPI == EPI_GATE_RESID) {
+                            const float4 x = xres[ps * 2 + it];
+                            o.x += x.x; o.y += x.y; o.z += x.z; o.w += x.w;
+                        }
+                        *dst = o;
+                    }
+                }
+            } else if constexpr (EPI == EPI_SWIGLU) {
+                // W rows interleaved in blocks of 16: columns [0,16) = w1 rows, [16,32) = w3 rows of hidden j0..j0+15
+                const int j0 = col / 2;
+                uint32_t w[16];     // words 0-7: hi halves of the 16 hidden values, 8-15: lo halves
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    split2(silu_fast(v[2 * i]) * v[16 + 2 * i], silu_fast(v[2 * i + 1]) * v[16 + 2 * i + 1], w[i], w[8 + i]);
+#pragma unroll
+                for (int ps = 0; ps < 2; ++ps) {
+                    stage8(w[ps * 8], w[ps * 8 + 1], w[ps * 8 + 2], w[ps * 8 + 3], w[ps * 8 + 4], w[ps * 8 + 5], w[ps * 8 + 6], w[ps * 8 + 7]);
+#ifndef PDK_DBG_NO_STORE
+                    __half* plane = ps == 0 ? p.ph : p.pl;
+#pragma unroll
+                    for (int it = 0; it < 2; ++it) {
+                        const uint4 u = unstage(it);
+                        *reinterpret_cast<uint4*>(plane + (size_t)(row0 + it * 16 + rr) * p.ldp + j0 + rc * 8) = u;
+                    }
+#endif
+                }
+            } else {   // EPI_QKV: this chunk is one head of q, k or v
+                const int which = col / p.c;
+                const int head = (col % p.c) / kHeadDim;
+                const int H = p.c / kHeadDim;
+                if (which < 2) {    // per-head RMSNorm (rms_norm.py:14-19); q additionally carries log2e/sqrt(32)
+                    float ss = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) ss = fmaf(v[i], v[i], ss);
+                    const float inv = (1.0f / sqrtf(ss * (1.0f / kHeadDim) + p.rms_eps)) * (which == 0 ? p.q_scale : 1.0f);
+                    const float* gain = which == 0 ? p.norm_q : p.norm_k;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 g4 = __ldg(reinterpret_cast<const float4*>(gain) + i);
+                        v[4 * i] *= inv * g4.x; v[4 * i + 1] *= inv * g4.y; v[4 * i + 2] *= inv * g4.z; v[4 * i + 3] *= inv * g4.w;
+                    }
+                }
+                __half* dbase = which == 0 ? p.q : (which == 1 ? p.k : p.v);      // row = [hi 32 | lo 32] halves = 128 bytes
+                const size_t tile_row = (size_t)(sample * H + head) * p.rows_per_sample + (row0 % p.rows_per_sample);
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) split2(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
+#pragma unroll
+                for (int ps = 0; ps < 4; ++ps) {      // 32-byte pieces of the 128-byte row: hi 0-15, hi 16-31, lo 0-15, lo 16-31
+                    const uint32_t* w = ps < 2 ? hi + (ps & 1) * 8 : lo + (ps & 1) * 8;
+                    stage8(w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7]);
+#pragma unroll
+                    for (int it = 0; it < 2; ++it) {
+                        const uint4 u = unstage(it);
+                        *reinterpret_cast<uint4*>(dbase + (tile_row + it * 16 + rr) * (2 * kHeadDim) + ps * 16 + rc * 8) = u;
+                    }
+                }
             }
         }
     }
@@ -365,7 +377,9 @@ cudaError_t launch_one(const GemmArgs& a, cudaStream_t st) {
         if ((e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
     }
     static const bool allow_pair = getenv("PDK_NO_PAIR") == nullptr;       // measurement switch
-    if (allow_pair && a.M % (2 * BM) == 0) return launch_variant<EPI, true>(a, st, num_sms);
+    static const bool force_pair = getenv("PDK_FORCE_PAIR") != nullptr;    // measurement switch
+    const bool big = (long long)a.K * a.N >= 700000;       // see the header: small-K shapes lose on the pair tiling
+    if (allow_pair && a.M % (2 * BM) == 0 && (big || force_pair)) return launch_variant<EPI, true>(a, st, num_sms);
     return launch_variant<EPI, false>(a, st, num_sms);
 }
 
