@@ -28,6 +28,10 @@
 #include "kernels.h"
 #include "umma.cuh"
 
+#include <algorithm>
+#include <mutex>
+#include <vector>
+
 namespace pdk {
 
 namespace {
@@ -50,7 +54,7 @@ constexpr uint32_t COL_S = 0, COL_O = 256;
 constexpr float kRescaleThreshold = 8.0f;            // log2 domain: P <= 2^8 stays exact enough in fp16 hi/lo
 
 // debug timeline: slot layout trace[(unit * 8 + k)]
-#define TRACE(unit, k) do { if (p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0) p.trace[(unit) * 8 + (k)] = clock64(); } while (0)
+#define TRACE(unit, k) do { if (p.trace != nullptr && blockIdx.x == 0 && lane == 0) p.trace[(unit) * 8 + (k)] = clock64(); } while (0)
 
 struct Bars {
     uint64_t q_full;
@@ -108,15 +112,26 @@ PDK_DEV void split2_pos(float p0, float p1, uint32_t& hi, uint32_t& lo) {
     asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(l1), "f"(l0));
 }
 
+// Work list: one entry per CTA = (head, query tile, first sample, number of samples <= G), packed 8 bits each, ordered
+// by decreasing sample count.  With the plain (B/G, S/128, H) grid the atom attention of the benchmark shape is 256
+// equal CTAs on 148 SMs = 1.73 waves (13% of the machine idle).  The host instead splits the B samples of some
+// (head, query tile) pairs into one more, smaller group (16 = 4+4+4+4 or 4+3+3+3+3) so that every SM gets one
+// 4-sample and one 3-sample CTA: 7 sample-units per SM instead of 8 (launch_attention below).
+constexpr int kMaxWork = 800;       // keeps the kernel parameters under 4 KB
+struct AttnWork {
+    uint32_t e[kMaxWork];
+};
+
 __global__ void __launch_bounds__(NTHREADS, 1)
 attention_umma_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUtensorMap mK,
-                      const __grid_constant__ CUtensorMap mV, const __grid_constant__ CUtensorMap mBias, const AttnArgs p) {
+                      const __grid_constant__ CUtensorMap mV, const __grid_constant__ CUtensorMap mBias, const AttnArgs p,
+                      const __grid_constant__ AttnWork work) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) Bars bars;
     __shared__ uint32_t tmem_slot;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b0 = blockIdx.x * G, qt = blockIdx.y, h = blockIdx.z;
-    const int ng = min(G, p.B - b0);
+    const uint32_t we = work.e[blockIdx.x];
+    const int h = (int)(we & 0xffu), qt = (int)((we >> 8) & 0xffu), b0 = p.b_base + (int)((we >> 16) & 0xffu), ng = (int)(we >> 24);
     const int S = p.S_pad;
     const int NJ = S / BKV;
     const uint32_t sm = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -374,14 +389,89 @@ attention_umma_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_const
 static long long* g_trace = nullptr;
 void set_attention_trace(long long* buf) { g_trace = buf; }
 
+namespace {
+
+// Greedy list scheduling (CTAs are dispatched in order to the first SM that frees up) of a work list in which `y`
+// of the (head, query tile) pairs use the finer sample partition: returns the makespan in sample-units.
+struct Partition { int n; int sizes[64]; };
+Partition make_partition(int B, int groups) {       // `groups` groups, sizes as even as possible
+    Partition pt{};
+    pt.n = groups;
+    for (int i = 0; i < groups; ++i) pt.sizes[i] = B / groups + (i < B % groups ? 1 : 0);
+    return pt;
+}
+double makespan(const std::vector<int>& sizes_desc, int sms, double fixed) {
+    std::vector<double> sm_free(sms, 0.0);
+    for (int sz : sizes_desc) {
+        int best = 0;
+        for (int i = 1; i < sms; ++i) if (sm_free[i] < sm_free[best]) best = i;
+        sm_free[best] += sz + fixed;
+    }
+    double m = 0;
+    for (double v : sm_free) m = v > m ? v : m;
+    return m;
+}
+
+struct WorkList { int B, H, QT, sms; int n; AttnWork w; };
+
+// Builds (and caches) the work list for a shape.  Returns nullptr when the shape needs more than kMaxWork CTAs.
+const WorkList* get_work_list(int B, int H, int QT, int sms) {
+    static std::mutex mu;
+    static std::vector<WorkList*> cache;
+    std::lock_guard<std::mutex> lock(mu);
+    for (const WorkList* w : cache) if (w->B == B && w->H == H && w->QT == QT && w->sms == sms) return w;
+    const int pairs = H * QT;
+    const int k0 = (B + G - 1) / G;
+    if (H > 255 || QT > 255 || B > 255 || (long long)pairs * (k0 + 1) > kMaxWork) return nullptr;
+    const Partition coarse = make_partition(B, k0);
+    const Partition fine = (k0 + 1 <= B) ? make_partition(B, k0 + 1) : coarse;
+    static const bool no_balance = getenv("PDK_NO_ATTN_BALANCE") != nullptr;      // measurement switch
+    const double fixed = 0.15;        // per-CTA prologue + epilogue in sample-units (one unit = all key tiles of one sample)
+    int best_y = 0;
+    double best = 1e30;
+    for (int y = 0; y <= (no_balance ? 0 : pairs); ++y) {
+        std::vector<int> sizes;
+        for (int pr = 0; pr < pairs; ++pr) {
+            const Partition& pt = pr < y ? fine : coarse;
+            for (int i = 0; i < pt.n; ++i) sizes.push_back(pt.sizes[i]);
+        }
+        std::sort(sizes.begin(), sizes.end(), [](int a, int b) { return a > b; });
+        const double m = makespan(sizes, sms, fixed);
+        if (m < best - 1e-9) { best = m; best_y = y; }
+    }
+    WorkList* wl = new WorkList{};
+    wl->B = B; wl->H = H; wl->QT = QT; wl->sms = sms;
+    struct Item { int ng, h, qt, b0; };
+    std::vector<Item> items;
+    // the pairs that use the fine partition are spread over heads and query tiles (pair index strided)
+    for (int pr = 0; pr < pairs; ++pr) {
+        const Partition& pt = pr < best_y ? fine : coarse;
+        const int h = pr % H, qt = pr / H;
+        int b0 = 0;
+        for (int i = 0; i < pt.n; ++i) { items.push_back({pt.sizes[i], h, qt, b0}); b0 += pt.sizes[i]; }
+    }
+    std::stable_sort(items.begin(), items.end(), [](const Item& a, const Item& b) { return a.ng > b.ng; });
+    wl->n = (int)items.size();
+    for (int i = 0; i < wl->n; ++i)
+        wl->w.e[i] = (uint32_t)items[i].h | ((uint32_t)items[i].qt << 8) | ((uint32_t)items[i].b0 << 16) | ((uint32_t)items[i].ng << 24);
+    cache.push_back(wl);
+    return wl;
+}
+
+}  // namespace
+
 cudaError_t launch_attention(const AttnArgs& a_in, cudaStream_t st) {
     AttnArgs a = a_in;
     a.trace = g_trace;
     if (a.S_pad <= 0 || a.S_pad % BQ || a.c != a.H * D || a.B <= 0) return cudaErrorInvalidValue;
     static bool configured = false;
+    static int num_sms = 0;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(attention_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (e != cudaSuccess) return e;
+        int dev = 0;
+        if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+        if ((e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
         configured = true;
     }
     const uint64_t rows = (uint64_t)a.B * a.H * a.S_pad;
@@ -391,8 +481,21 @@ cudaError_t launch_attention(const AttnArgs& a_in, cudaStream_t st) {
     if ((e = get_tensor_map_f16(a.k, rows, 2 * D, 2 * D, BKV, 2 * D, 128, &mK)) != cudaSuccess) return e;
     if ((e = get_tensor_map_f16(a.v, rows, 2 * D, 2 * D, BKV, 2 * D, 128, &mV)) != cudaSuccess) return e;
     if ((e = get_tensor_map_f32(a.bias, (uint64_t)a.H * a.S_pad, a.S_pad, a.S_pad, BQ, 32, 128, &mBias)) != cudaSuccess) return e;
-    dim3 grid((a.B + G - 1) / G, a.S_pad / BQ, a.H);
-    PDK_LAUNCH_CHECK(launch_pdl(attention_umma_kernel, grid, dim3(NTHREADS), (size_t)SMEM_BYTES, st, mQ, mK, mV, mBias, a));
+    // Samples are processed in chunks of <= 255 (8-bit fields of the work list); shapes whose list does not fit in the
+    // kernel parameters are launched as several lists.
+    const int QT = a.S_pad / BQ;
+    int b_done = 0;
+    while (b_done < a.B) {
+        int bc = a.B - b_done;
+        if (bc > 252) bc = 252;
+        while ((long long)a.H * QT * ((bc + G - 1) / G + 1) > kMaxWork && bc > G) bc = ((bc / 2 + G - 1) / G) * G;
+        const WorkList* wl = get_work_list(bc, a.H, QT, num_sms);
+        if (wl == nullptr) return cudaErrorInvalidValue;      // H * QT alone exceeds the list: not a PhysDock shape
+        AttnArgs c = a;
+        c.b_base = b_done;
+        PDK_LAUNCH_CHECK(launch_pdl(attention_umma_kernel, dim3(wl->n), dim3(NTHREADS), (size_t)SMEM_BYTES, st, mQ, mK, mV, mBias, c, wl->w));
+        b_done += bc;
+    }
     return cudaGetLastError();
 }
 

@@ -115,7 +115,7 @@ int run_block(const pdk_dit& h, const pdk_block_weights& bw, const Workspace& ws
     g.norm_q = bw.norm_q; g.norm_k = bw.norm_k; g.c = c; g.rows_per_sample = (int)Sp;
     g.rms_eps = eps; g.q_scale = kLog2e / sqrtf((float)kHeadDim);
     PDK_TRY("gemm(qkv)", launch_gemm(EPI_QKV, g, st));
-    AttnArgs at{ws.q, ws.k, ws.v, bias, ws.oh, ws.ol, (int)B, Hh, (int)Sp, c, nullptr};
+    AttnArgs at{ws.q, ws.k, ws.v, bias, ws.oh, ws.ol, (int)B, Hh, (int)Sp, c, 0, nullptr};
     PDK_TRY("attention", launch_attention(at, st));
     g = GemmArgs{};
     g.Ah = ws.oh; g.Al = ws.ol; g.lda = c;
@@ -405,7 +405,7 @@ int pdk_op_gemm_qkv(const void* Ah, const void* Al, int64_t lda, const void* Wh,
 }
 int pdk_op_attention(const void* q, const void* k, const void* v, const float* bias, void* oh, void* ol, int64_t B,
                      int64_t Hh, int64_t S_pad, void* stream) {
-    AttnArgs a{H(q), H(k), H(v), bias, H(oh), H(ol), (int)B, (int)Hh, (int)S_pad, (int)(Hh * kHeadDim), nullptr};
+    AttnArgs a{H(q), H(k), H(v), bias, H(oh), H(ol), (int)B, (int)Hh, (int)S_pad, (int)(Hh * kHeadDim), 0, nullptr};
     PDK_TRY("attention", launch_attention(a, S(stream)));
     return 0;
 }

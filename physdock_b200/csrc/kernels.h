@@ -42,6 +42,7 @@ struct AttnArgs {
     const float* bias;
     __half* oh; __half* ol;
     int B, H, S_pad, c;
+    int b_base;         // set by launch_attention: first sample of the launched chunk
     long long* trace;   // debug only: per-unit clock64 stamps of CTA (0,0,0); nullptr in production
 };
 cudaError_t launch_attention(const AttnArgs& a, cudaStream_t st);

@@ -52,7 +52,7 @@ def test_gemm_store_vs_fp64(M, N, K):
     rel_close("gemm_store+silu", got, F.silu(A.double() @ W.double().t()), rtol=0, atol=atol)
 
 
-@pytest.mark.parametrize("B,H,S", [(1, 4, 128), (2, 4, 384), (2, 16, 256)])
+@pytest.mark.parametrize("B,H,S", [(1, 4, 128), (2, 4, 384), (2, 16, 256), (5, 4, 256), (7, 16, 128), (9, 4, 640)])
 def test_attention_vs_fp64(B, H, S):
     from physdock_b200 import ops
     g = torch.Generator().manual_seed(B * 1000 + S)
