@@ -124,6 +124,22 @@ int pdk_template_select(const float* x_den, const int32_t* lig_idx, const float*
 int pdk_rigid_align(const float* x_den, const float* x_exists, const float* x_gt, int gt_batched, const float* w,
                     float* aligned, int64_t B, int64_t Na, void* stream);
 
+/* Pair-energy physics backend (opt-in, device-resident replacement of get_next_step_pos, model.py:26-52, whose
+ * RDKit MMFF94 arithmetic is not part of the reference tree; functional form defined in csrc/physics.cu, oracle =
+ * autograd restatement oracle/physdock_oracle.py:pair_energy).
+ *   rows [n_rows] / in_rows [Na] (both or neither): the movable atoms (ligand); NULL = every atom, n_rows = Na.
+ *   partner / partner_r0 / partner_k [Na,E]: symmetric bonded-partner table, -1 = empty slot; listed pairs are excluded
+ *   from the nonbonded terms and carry k (d - r0)^2 when k != 0.
+ *   e_row [B,n_rows], energy [B] (may be NULL), grad [B,Na,3] (rows of non-row atoms are not written). */
+int pdk_pair_energy_grad(const float* x, const float* x_exists, const float* sigma, const float* eps,
+                         const int32_t* partner, const float* partner_r0, const float* partner_k, int64_t E,
+                         const int32_t* rows, const uint8_t* in_rows, int64_t n_rows, float clash_k, float clash_scale,
+                         float cutoff, float softcore, float* e_row, float* energy, float* grad, int64_t B, int64_t Na,
+                         void* stream);
+/* One projected-gradient step: x_out = x - step * clamp(grad, +-gmax) on the row atoms, copy elsewhere. */
+int pdk_descent_update(const float* x, const float* grad, const uint8_t* in_rows, float step, float gmax, float* x_out,
+                       int64_t B, int64_t Na, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Op-level entry points (one kernel each) -- what pdk_dit_denoise is built from; exported so the parity
  * tests can check every kernel against the oracle in isolation.

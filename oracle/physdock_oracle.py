@@ -399,6 +399,88 @@ def sample_diffusion(sd: State, batch: Dict[str, Tensor], a: Tensor, ap: Tensor,
     return x_next
 
 
+# ----------------------------------------------------------------------------------------------
+# pair-energy physics backend (extension; NOT reference arithmetic)
+# ----------------------------------------------------------------------------------------------
+def pair_energy(x: Tensor, x_exists: Tensor, sigma: Tensor, eps: Tensor, partner: Optional[Tensor],
+                partner_r0: Optional[Tensor], partner_k: Optional[Tensor], rows: Optional[Tensor],
+                clash_k: float = 10.0, clash_scale: float = 0.6, cutoff: float = 10.0,
+                softcore: float = 0.1) -> Tensor:
+    """Restatement of the functional form DEFINED in physdock_b200/csrc/physics.cu (header comment) as dense
+    differentiable tensor algebra; its gradient comes from autograd.  This is the checker of the opt-in physics backend
+    that replaces get_next_step_pos (models/model.py:26-52, RDKit MMFF94, parity unpinned): the reference has no
+    arithmetic for it (its lj/bond losses are stubs, models/loss_module.py:284-308).
+
+    x [B,Na,3]; rows [n] (None = all atoms); partner tables [Na,E] (-1 = empty).  Returns energy [B].
+    """
+    B, Na, _ = x.shape
+    dt = x.dtype
+    if rows is None:
+        rows = torch.arange(Na)
+    rows = rows.long()
+    in_rows = torch.zeros(Na, dtype=torch.bool)
+    in_rows[rows] = True
+    xi = x[:, rows]                                                     # [B,n,3]
+    diff = xi[:, :, None, :] - x[:, None, :, :]                         # [B,n,Na,3]
+    r2 = (diff ** 2).sum(-1)
+    d2 = r2 + 1e-12
+    d = torch.sqrt(d2)
+    ex = x_exists.to(dt)
+    sig = 0.5 * (sigma[rows][:, None] + sigma[None, :]).to(dt)          # [n,Na]
+    se = torch.sqrt(eps.clamp(min=0).to(dt))
+    e_ij = se[rows][:, None] * se[None, :]
+    nb = (ex[rows][:, None] * ex[None, :]).bool()
+    excl = torch.zeros(len(rows), Na, dtype=torch.bool)
+    excl[torch.arange(len(rows)), rows] = True
+    if partner is not None and partner.numel() > 0:
+        pr = partner[rows].long()                                       # [n,E]
+        valid = pr >= 0
+        ri = torch.arange(len(rows))[:, None].expand_as(pr)
+        excl[ri[valid], pr[valid]] = True
+    nb = nb & ~excl
+    nbf = (nb[None] & (r2.detach() < cutoff * cutoff)).to(dt)           # the cutoff is a hard mask (no switching)
+    sig2 = sig ** 2
+    u = sig2 / (d2 + softcore * sig2)
+    s6 = u ** 3
+    e_lj = e_ij * (s6 * s6 - 2.0 * s6)
+    pen = torch.clamp(clash_scale * sig - d, min=0.0)
+    e_nb = (e_lj + clash_k * pen * pen) * nbf
+    w = torch.where(in_rows, 0.5, 1.0).to(dt)[None, None, :]
+    energy = (w * e_nb).sum(dim=(1, 2))
+    if partner is not None and partner.numel() > 0:
+        pr = partner[rows].long()
+        valid = (pr >= 0)
+        prc = pr.clamp(min=0)
+        xj = x[:, prc]                                                  # [B,n,E,3]
+        db = torch.sqrt(((xi[:, :, None, :] - xj) ** 2).sum(-1) + 1e-12)
+        k = partner_k[rows].to(dt) * valid.to(dt) * ex[rows][:, None] * ex[prc]
+        wb = torch.where(in_rows[prc], 0.5, 1.0).to(dt)
+        energy = energy + (wb * k * (db - partner_r0[rows].to(dt)) ** 2).sum(dim=(1, 2))
+    return energy
+
+
+def pair_energy_grad(x: Tensor, *args, **kw):
+    """(energy [B], dE/dx [B,Na,3]) by autograd; the backend only reports the rows' gradient."""
+    xg = x.detach().clone().requires_grad_(True)
+    with torch.enable_grad():
+        e = pair_energy(xg, *args, **kw)
+        g, = torch.autograd.grad(e.sum(), xg)
+    return e.detach(), g
+
+
+def pair_energy_descend(x: Tensor, x_exists, sigma, eps, partner, partner_r0, partner_k, rows, iters: int = 5,
+                        step: float = 0.01, gmax: float = 50.0, **kw) -> Tensor:
+    """`iters` clamped gradient-descent steps on the row atoms (the backend's stand-in for MMFFOptimizeMolecule(maxIters))."""
+    Na = x.shape[1]
+    mask = torch.zeros(Na, dtype=x.dtype)
+    mask[(torch.arange(Na) if rows is None else rows.long())] = 1
+    cur = x.clone()
+    for _ in range(iters):
+        _, g = pair_energy_grad(cur, x_exists, sigma, eps, partner, partner_r0, partner_k, rows, **kw)
+        cur = cur - step * g.clamp(-gmax, gmax) * mask[None, :, None]
+    return cur
+
+
 def rmsd(a: Tensor, b: Tensor) -> Tensor:
     """Per-sample RMSD in Angstrom between two coordinate sets [B,N,3] (the parity metric)."""
     return ((a.double() - b.double()) ** 2).sum(-1).mean(-1).sqrt()

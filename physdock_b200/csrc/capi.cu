@@ -329,6 +329,28 @@ int pdk_template_select(const float* x_den, const int32_t* lig_idx, const float*
     return 0;
 }
 
+int pdk_pair_energy_grad(const float* x, const float* x_exists, const float* sigma, const float* eps,
+                         const int32_t* partner, const float* partner_r0, const float* partner_k, int64_t E,
+                         const int32_t* rows, const uint8_t* in_rows, int64_t n_rows, float clash_k, float clash_scale,
+                         float cutoff, float softcore, float* e_row, float* energy, float* grad, int64_t B, int64_t Na,
+                         void* stream) {
+    if (!x || !x_exists || !sigma || !eps || !e_row || !grad) return fail_msg("pdk_pair_energy_grad", "null argument");
+    if (E > 0 && (!partner || !partner_r0 || !partner_k)) return fail_msg("pdk_pair_energy_grad", "partner table missing");
+    if ((rows == nullptr) != (in_rows == nullptr)) return fail_msg("pdk_pair_energy_grad", "rows and in_rows go together");
+    if (rows == nullptr && n_rows != Na) return fail_msg("pdk_pair_energy_grad", "n_rows must equal Na when rows is NULL");
+    const PairEnergyParams pp{clash_k, clash_scale, cutoff * cutoff, softcore};
+    PDK_TRY("pair_energy_grad", launch_pair_energy_grad(x, x_exists, sigma, eps, partner, partner_r0, partner_k, (int)E, rows,
+                                                        in_rows, (int)n_rows, e_row, energy, grad, (int)B, (int)Na, pp, S(stream)));
+    return 0;
+}
+
+int pdk_descent_update(const float* x, const float* grad, const uint8_t* in_rows, float step, float gmax, float* x_out,
+                       int64_t B, int64_t Na, void* stream) {
+    if (!x || !grad || !x_out) return fail_msg("pdk_descent_update", "null argument");
+    PDK_TRY("descent_update", launch_descent_update(x, grad, in_rows, step, gmax, x_out, (int)B, (int)Na, S(stream)));
+    return 0;
+}
+
 int pdk_rigid_align(const float* x_den, const float* x_exists, const float* x_gt, int gt_batched, const float* w,
                     float* aligned, int64_t B, int64_t Na, void* stream) {
     if (!x_den || !x_exists || !x_gt || !w || !aligned) return fail_msg("pdk_rigid_align", "null argument");

@@ -97,4 +97,20 @@ cudaError_t launch_template_pick(const float* eps, const float* ref_poses, const
 cudaError_t launch_rigid_align(const float* x_pred, const float* x_exists, const float* x_gt, int gt_batched,
                                const float* w, float* aligned, int B, int Na, cudaStream_t st);
 
+// ----------------------------------------------------------------------------- pair-energy physics backend (physics.cu)
+struct PairEnergyParams {
+    float clash_k;       // clash penalty weight
+    float clash_scale;   // clash when d < clash_scale * sig_ij
+    float cutoff2;       // squared nonbonded cutoff
+    float softcore;      // soft-core constant of the LJ term
+};
+// Energy of the row atoms in the field of all atoms, per-row energies e_row[B,n_rows], energy[B] (optional) and
+// grad[B,Na,3] (written for row atoms only).  partner/p_r0/p_k [Na,E]: bonded-partner table (-1 = empty slot).
+cudaError_t launch_pair_energy_grad(const float* x, const float* exists, const float* sigma, const float* eps,
+                                    const int* partner, const float* p_r0, const float* p_k, int E, const int* rows,
+                                    const unsigned char* in_rows, int n_rows, float* e_row, float* energy, float* grad,
+                                    int B, int Na, const PairEnergyParams& pp, cudaStream_t st);
+cudaError_t launch_descent_update(const float* x, const float* grad, const unsigned char* in_rows, float step, float gmax,
+                                  float* x_out, int B, int Na, cudaStream_t st);
+
 }  // namespace pdk

@@ -144,7 +144,8 @@ class DiffusionSampler:
                  ref_mol_poses: Optional[torch.Tensor] = None, use_ref_mol_poses: bool = False,
                  mmff_gamma_0_factor: float = 1.0, mmff_iters: int = 5, align_ref_pos: bool = True,
                  karras_noise_schedule_power: float = 7, rng=None, mmff_fn: Optional[Callable] = None,
-                 use_cuda_graph: bool = True):
+                 use_cuda_graph: bool = True, physics_field=None, physics_step: float = 0.002,
+                 physics_gmax: float = 50.0):
         dev = batch["x_gt"].device
         self.use_cuda_graph = use_cuda_graph and os.environ.get("PDK_NO_GRAPH") is None
         if dev.type != "cuda":
@@ -172,6 +173,9 @@ class DiffusionSampler:
         if ref_mol is not None and mmff_fn is None:
             mmff_fn = _rdkit_mmff(ref_mol, mmff_iters)
         self.mmff_fn = mmff_fn
+        # opt-in device-resident replacement of the MMFF step (physics.PairEnergyField); takes precedence over mmff_fn
+        self.physics_field, self.mmff_iters = physics_field, mmff_iters
+        self.physics_step, self.physics_gmax = physics_step, physics_gmax
         dit._pack()
         sig = dit._complex_signature(batch, a, ap, s, z)
         if sig != dit._complex_sig:
@@ -228,6 +232,12 @@ class DiffusionSampler:
                                                     self.batch_ref_pos)
             weighted_rigid_align(self.x_den, self.x_exists, self.batch_ref_pos, self.weights, out=self.aligned)
             physics = True
+        elif self.physics_field is not None and bool(t_cur <= self.gamma_min * self.mmff_factor):
+            # model.py:252-261 with get_next_step_pos replaced by mmff_iters descent steps on the pair energy (GPU)
+            x_ref = self.physics_field.descend(self.x_den, iters=self.mmff_iters, step=self.physics_step,
+                                               gmax=self.physics_gmax)
+            weighted_rigid_align(self.x_den, self.x_exists, x_ref, self.weights, out=self.aligned)
+            physics = True
         elif self.mmff_fn is not None and bool(t_cur <= self.gamma_min * self.mmff_factor):
             x_ref = self.x_den.clone()
             x_ref[:, self.is_ligand_atom] = self.mmff_fn(self.x_den[:, self.is_ligand_atom])
@@ -260,10 +270,12 @@ def sample_diffusion(dit: B200DiT, batch: Dict[str, torch.Tensor], a, ap, s, z, 
                      use_ref_mol_poses: bool = False, mmff_gamma_0_factor: float = 1.0, mmff_iters: int = 5,
                      align_ref_pos: bool = True, karras_noise_schedule_power: float = 7, rng=None,
                      mmff_fn: Optional[Callable] = None, trace: Optional[List[dict]] = None,
-                     teacher: Optional[List[dict]] = None, max_steps: Optional[int] = None) -> torch.Tensor:
+                     teacher: Optional[List[dict]] = None, max_steps: Optional[int] = None, physics_field=None,
+                     physics_step: float = 0.002, physics_gmax: float = 50.0) -> torch.Tensor:
     """`PhysDock.sample_diffusion` (model.py:157-282) given the trunk outputs (a, ap, s, z).
 
-    Extra hooks (not in the reference): `rng` (object with rand/normal), `mmff_fn`, `trace` (list that
+    Extra hooks (not in the reference): `rng` (object with rand/normal), `mmff_fn`, `physics_field` (a
+    physics.PairEnergyField: GPU replacement of the MMFF step), `trace` (list that
     receives per-step tensors), `teacher` (per-step dicts with an `x_hat` to feed the denoiser instead of the
     free-running one: teacher-forced parity).
     """
@@ -272,7 +284,8 @@ def sample_diffusion(dit: B200DiT, batch: Dict[str, torch.Tensor], a, ap, s, z, 
                            ode_step_scale_eta=ode_step_scale_eta, ref_mol=ref_mol, ref_mol_poses=ref_mol_poses,
                            use_ref_mol_poses=use_ref_mol_poses, mmff_gamma_0_factor=mmff_gamma_0_factor,
                            mmff_iters=mmff_iters, align_ref_pos=align_ref_pos,
-                           karras_noise_schedule_power=karras_noise_schedule_power, rng=rng, mmff_fn=mmff_fn)
+                           karras_noise_schedule_power=karras_noise_schedule_power, rng=rng, mmff_fn=mmff_fn,
+                           physics_field=physics_field, physics_step=physics_step, physics_gmax=physics_gmax)
     x = smp.begin()
     for i in range(steps):
         if max_steps is not None and i >= max_steps:

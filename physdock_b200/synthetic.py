@@ -20,6 +20,8 @@ from collections import OrderedDict
 from dataclasses import dataclass, asdict
 from typing import Dict, Optional
 
+import math
+
 import torch
 
 
@@ -201,6 +203,45 @@ def make_templates(batch: Dict[str, torch.Tensor], n_templates: int = 40, seed: 
     base = batch["x_gt"].cpu()[lig]
     t = base[None] + jitter * torch.randn(n_templates, base.shape[0], 3, generator=g)
     return t.to(batch["x_gt"].device)
+
+
+def make_ligand_field(Na: int, n_lig: int, seed: int = 0, missing: bool = True) -> Dict[str, torch.Tensor]:
+    """Synthetic input of the pair-energy physics backend (physics.py): a globule of `Na - n_lig` "protein" atoms
+    (jittered 1.9 A lattice points nearest the origin) and a bonded chain of `n_lig` ligand atoms (the LAST atoms, as in
+    PhysDock crops where ligand tokens come last) threaded through it.  Returns x0 [Na,3], x_exists, per-atom sigma/eps
+    (three pseudo-elements), the symmetric partner table of the ligand (1-2 bonds k=300 r0=1.5, 1-3 restraints k=40,
+    one pure exclusion), rows (ligand atom indices, int32) and in_rows (bool)."""
+    from .physics import build_partner_table
+    g = torch.Generator().manual_seed(seed)
+    n_prot = Na - n_lig
+    side = int(math.ceil((2.2 * n_prot) ** (1 / 3))) + 2
+    ax = (torch.arange(side, dtype=torch.float32) - (side - 1) / 2) * 1.9
+    grid = torch.stack(torch.meshgrid(ax, ax, ax, indexing="ij"), dim=-1).reshape(-1, 3)
+    order = torch.argsort((grid ** 2).sum(-1), stable=True)
+    prot = grid[order[:n_prot]] + 0.25 * torch.randn(n_prot, 3, generator=g)
+    lig = torch.zeros(n_lig, 3)
+    direction = torch.tensor([1.0, 0.3, -0.2])
+    for i in range(1, n_lig):
+        step = direction + 0.9 * torch.randn(3, generator=g)
+        lig[i] = lig[i - 1] + 1.5 * step / step.norm()
+    lig = lig - lig.mean(0) + torch.tensor([0.4, -0.3, 0.2])
+    x0 = torch.cat([prot, lig], dim=0)
+    kind = torch.randint(0, 3, (Na,), generator=g)
+    sigma = torch.tensor([3.4, 3.1, 3.8])[kind]
+    eps = torch.tensor([0.09, 0.17, 0.05])[kind]
+    x_exists = torch.ones(Na)
+    if missing and n_prot > 8:
+        x_exists[torch.randperm(n_prot, generator=g)[:max(1, n_prot // 50)]] = 0
+    bonds = [(n_prot + i, n_prot + i + 1, 1.5, 300.0) for i in range(n_lig - 1)]
+    bonds += [(n_prot + i, n_prot + i + 2, 2.45, 40.0) for i in range(n_lig - 2)]
+    if n_lig >= 5:
+        bonds.append((n_prot, n_prot + 4, 0.0, 0.0))        # exclusion without a restraint
+    partner, r0, k = build_partner_table(Na, bonds)
+    rows = torch.arange(n_prot, Na, dtype=torch.int32)
+    in_rows = torch.zeros(Na, dtype=torch.bool)
+    in_rows[n_prot:] = True
+    return dict(x0=x0, x_exists=x_exists, sigma=sigma, eps=eps, partner=partner, partner_r0=r0, partner_k=k, rows=rows,
+                in_rows=in_rows)
 
 
 def checksum(t: torch.Tensor) -> float:

@@ -135,3 +135,45 @@ def test_sharded_sampler_single_rank_equals_plain(dit):
     b = sample_diffusion_sharded(dit, cx, cx["a"], cx["ap"], cx["s"], cx["z"], num_sample=3, seed=11, steps=5,
                                  karras_noise_schedule_power=1000, align_ref_pos=False)
     assert torch.equal(a, b)
+
+
+def test_late_step_with_pair_energy_field(dit):
+    """Late steps (t_cur <= gamma_min * factor) with the opt-in GPU physics backend: x_next must equal the oracle's
+    composition descend -> weighted_rigid_align -> blended direction -> Euler applied to the same x_denoised."""
+    from physdock_b200 import sampler as S
+    from physdock_b200.physics import PairEnergyField
+    from physdock_b200.synthetic import make_ligand_field
+    cx = complex_64_512()
+    d = to_dev(cx)
+    Na = cx["x_gt"].shape[0]
+    lig = cx["is_ligand"][cx["atom_id_to_token_id"]].bool()
+    rows = torch.nonzero(lig).flatten().int()
+    n_lig = int(rows.numel())
+    f = make_ligand_field(Na, n_lig, seed=2, missing=False)
+    # the field's bonded chain sits on the complex's ligand atoms (synthetic layout: ligand tokens come last)
+    assert torch.equal(rows, f["rows"])
+    fld = PairEnergyField(d["a_mask"], f["sigma"], f["eps"], f["partner"], f["partner_r0"], f["partner_k"], rows=rows)
+    torch.manual_seed(4)
+    smp = S.DiffusionSampler(dit, d, d["a"], d["ap"], d["s"], d["z"], num_sample=3, steps=12,
+                             karras_noise_schedule_power=1000, align_ref_pos=True, mmff_gamma_0_factor=6.0,
+                             mmff_iters=5, physics_field=fld, physics_step=0.002)
+    smp.begin()
+    late = [i for i in range(12) if float(smp.sigmas[i]) <= 6.0]
+    assert late, "schedule has no late step"
+    i = late[0]
+    # a plausible late-step state: ligand chain + globule with noise at the step's sigma
+    g = torch.Generator().manual_seed(9)
+    smp.x_next = (f["x0"][None] + float(smp.sigmas[i]) * torch.randn(3, Na, 3, generator=g)).to(DEV).contiguous()
+    x_next = smp.step(i).cpu()
+    x_hat, x_den = smp.x_hat.cpu(), smp.x_den.cpu()
+    t_cur, t_next, t_hat, stochastic, _ = smp.schedule(i)
+    args = (cx["a_mask"], f["sigma"], f["eps"], f["partner"], f["partner_r0"], f["partner_k"], rows)
+    x_ref = O.pair_energy_descend(x_den, *args, iters=5, step=0.002, gmax=50.0)
+    w = cx["a_mask"] * lig.float()
+    aligned = O.weighted_rigid_align(x_den * cx["a_mask"][..., None], x_ref, w)
+    th = torch.full([3], float(t_hat))
+    d_cur = O.physics_direction(x_hat, x_den, aligned, th, w)
+    want = O.euler_update(x_hat, d_cur, th, t_next, 1.5 if stochastic else 1.0)
+    r = float(O.rmsd(x_next, want).max())
+    log_value("late step with pair-energy field: x_next rmsd vs oracle composition", r)
+    assert r < TOL_A, r
