@@ -124,6 +124,9 @@ int pdk_template_select(const float* x_den, const int32_t* lig_idx, const float*
 int pdk_rigid_align(const float* x_den, const float* x_exists, const float* x_gt, int gt_batched, const float* w,
                     float* aligned, int64_t B, int64_t Na, void* stream);
 
+/* Pose ranking (redocking.py:391): dist[S,S] (fp64) = sqrt(mean over the n ligand atoms of |pose_s - pose_t|^2). */
+int pdk_pairwise_rmsd(const float* poses, double* dist, int64_t S, int64_t n, void* stream);
+
 /* Pair-energy physics backend (opt-in, device-resident replacement of get_next_step_pos, model.py:26-52, whose
  * RDKit MMFF94 arithmetic is not part of the reference tree; functional form defined in csrc/physics.cu, oracle =
  * autograd restatement oracle/physdock_oracle.py:pair_energy).

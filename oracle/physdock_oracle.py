@@ -481,6 +481,62 @@ def pair_energy_descend(x: Tensor, x_exists, sigma, eps, partner, partner_r0, pa
     return cur
 
 
+# ----------------------------------------------------------------------------------------------
+# caller-side ranking (redocking.py), numpy as in the reference
+# ----------------------------------------------------------------------------------------------
+def pairwise_pose_rmsd(pred) -> "np.ndarray":
+    """redocking.py:391.  pred [S,n,3] -> [S,S] float64."""
+    import numpy as np
+    pred = np.asarray(pred, dtype=np.float64)
+    return np.sqrt(np.mean(np.linalg.norm(pred[:, None] - pred[None], axis=-1) ** 2, axis=-1))
+
+
+def get_representatives(distance_matrix, num_clusters: int = 5):
+    """redocking.py:393-410 (sklearn KMeans, random_state=0; medoid per cluster)."""
+    import numpy as np
+    from sklearn.cluster import KMeans
+    num_elements = len(distance_matrix)
+    coordinates = np.zeros((num_elements, num_elements))
+    for i in range(num_elements):
+        coordinates[i] = distance_matrix[i]
+    kmeans = KMeans(n_clusters=num_clusters, random_state=0)
+    kmeans.fit(coordinates)
+    labels = kmeans.labels_
+    representatives_indices = []
+    for cluster_id in range(num_clusters):
+        cluster_indices = np.where(labels == cluster_id)[0]
+        avg_distances = np.mean(distance_matrix[cluster_indices, :], axis=0)
+        representatives_indices.append(cluster_indices[np.argmin(avg_distances[cluster_indices])])
+    return [int(i) for i in representatives_indices]
+
+
+def rank_poses(pred, num_clusters: int = 5):
+    """redocking.py:412-423."""
+    dist = pairwise_pose_rmsd(pred)
+    if len(dist) > num_clusters:
+        ids = get_representatives(dist, num_clusters)
+        ids_1 = get_representatives(dist, 1)[0]
+        if ids_1 in ids:
+            ids.remove(ids_1)
+            ids = [ids_1] + ids
+        else:
+            ids = [ids_1] + ids[:4]
+    else:
+        ids = list(range(len(dist)))
+    return ids, dist
+
+
+def rank_conformer_templates(x_pred_lig: Tensor, ref_mol_poses: Tensor, n_keep: int) -> Tensor:
+    """redocking.py:326-332."""
+    ref_mol_poses_dist = torch.norm(ref_mol_poses[:, :, None] - ref_mol_poses[:, None], dim=-1)
+    ligand_dist = torch.norm(x_pred_lig[:, :, None] - x_pred_lig[:, None], dim=-1)
+    delta = (ligand_dist[:, None] - ref_mol_poses_dist[None]).abs()
+    epsilon = 0.25 * (torch.sigmoid(-0.5 + delta) + torch.sigmoid(-1 + delta) + torch.sigmoid(
+        -2 + delta) + torch.sigmoid(-4 + delta))
+    epsilon = epsilon.mean(dim=[-1, -2, -4])
+    return torch.argsort(epsilon)[:n_keep]
+
+
 def rmsd(a: Tensor, b: Tensor) -> Tensor:
     """Per-sample RMSD in Angstrom between two coordinate sets [B,N,3] (the parity metric)."""
     return ((a.double() - b.double()) ** 2).sum(-1).mean(-1).sqrt()

@@ -329,6 +329,12 @@ int pdk_template_select(const float* x_den, const int32_t* lig_idx, const float*
     return 0;
 }
 
+int pdk_pairwise_rmsd(const float* poses, double* dist, int64_t n_poses, int64_t n, void* stream) {
+    if (!poses || !dist) return fail_msg("pdk_pairwise_rmsd", "null argument");
+    PDK_TRY("pairwise_rmsd", launch_pairwise_rmsd(poses, dist, (int)n_poses, (int)n, S(stream)));
+    return 0;
+}
+
 int pdk_pair_energy_grad(const float* x, const float* x_exists, const float* sigma, const float* eps,
                          const int32_t* partner, const float* partner_r0, const float* partner_k, int64_t E,
                          const int32_t* rows, const uint8_t* in_rows, int64_t n_rows, float clash_k, float clash_scale,

@@ -340,4 +340,33 @@ cudaError_t launch_rigid_align(const float* x_den, const float* x_exists, const 
     return cudaGetLastError();
 }
 
+// Pairwise pose RMSD matrix used for ranking (redocking.py:391:
+//   dist = sqrt(mean_atoms(|pred[:,None] - pred[None]|^2))), fp64 accumulation.  One warp per (s, t) pair.
+namespace {
+__global__ void __launch_bounds__(256) pairwise_rmsd_kernel(const float* __restrict__ poses, double* __restrict__ dist, int S, int n) {
+    griddep_launch();
+    griddep_wait();
+    const int pair = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (pair >= S * S) return;
+    const int a = pair / S, b = pair % S;
+    const float* pa = poses + (size_t)a * n * 3;
+    const float* pb = poses + (size_t)b * n * 3;
+    double acc = 0.0;
+    for (int i = lane; i < n; i += 32) {
+        const double dx = (double)pa[3 * i] - (double)pb[3 * i], dy = (double)pa[3 * i + 1] - (double)pb[3 * i + 1],
+                     dz = (double)pa[3 * i + 2] - (double)pb[3 * i + 2];
+        const double nrm = sqrt(dx * dx + dy * dy + dz * dz);      // np.linalg.norm(...) ** 2, as the reference writes it
+        acc += nrm * nrm;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) dist[pair] = sqrt(acc / (double)n);
+}
+}  // namespace
+
+cudaError_t launch_pairwise_rmsd(const float* poses, double* dist, int S, int n, cudaStream_t st) {
+    if (S <= 0 || n <= 0) return cudaErrorInvalidValue;
+    PDK_LAUNCH_CHECK(launch_pdl(pairwise_rmsd_kernel, dim3((S * S + 7) / 8), dim3(256), (size_t)0, st, poses, dist, S, n));
+    return cudaGetLastError();
+}
+
 }  // namespace pdk

@@ -97,6 +97,9 @@ cudaError_t launch_template_pick(const float* eps, const float* ref_poses, const
 cudaError_t launch_rigid_align(const float* x_pred, const float* x_exists, const float* x_gt, int gt_batched,
                                const float* w, float* aligned, int B, int Na, cudaStream_t st);
 
+// dist[S,S] (fp64) = pairwise RMSD of poses [S,n,3]  (ranking, redocking.py:391)
+cudaError_t launch_pairwise_rmsd(const float* poses, double* dist, int S, int n, cudaStream_t st);
+
 // ----------------------------------------------------------------------------- pair-energy physics backend (physics.cu)
 struct PairEnergyParams {
     float clash_k;       // clash penalty weight

@@ -82,3 +82,31 @@ def sample_diffusion_sharded(dit, batch, a, ap, s, z, num_sample: int, seed: int
         pass    # templates are shared by all samples: nothing to shard
     x_local = sample_diffusion(dit, batch, a, ap, s, z, num_sample=hi - lo, rng=rng, **kw)
     return gather_samples(x_local)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# screening (reference screening.py:106-119 loops over the ligand library in ONE process)
+# ---------------------------------------------------------------------------------------------------------------------
+def shard_ligands(n_ligands: int, rank: int, world_size: int):
+    """Round-robin split of a ligand library: rank r screens ligands r, r+ws, r+2ws, ...; all `num_sample` poses of one
+    ligand stay on one GPU (they share that ligand's trunk outputs and pair-bias cache)."""
+    return list(range(rank, n_ligands, world_size))
+
+
+def screen_library(n_ligands: int, sample_ligand, n_atoms_of=None):
+    """Runs `sample_ligand(ligand_index) -> x [num_sample, n_atoms, 3]` for this rank's ligands and returns, on every
+    rank, the list of all ligands' coordinates in library order.  No collective on the data path; ONE all_gather_object
+    of the (small) final coordinates per library.  `n_atoms_of` is unused (kept for symmetric signatures)."""
+    rank, ws = world()
+    mine = shard_ligands(n_ligands, rank, ws)
+    local = [(i, sample_ligand(i).detach().cpu()) for i in mine]
+    if ws == 1:
+        gathered = [local]
+    else:
+        gathered = [None] * ws
+        dist.all_gather_object(gathered, local)
+    out = [None] * n_ligands
+    for part in gathered:
+        for i, x in part:
+            out[i] = x
+    return out

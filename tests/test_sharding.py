@@ -57,3 +57,43 @@ def test_two_rank_gather_equals_single_process():
     x0 = torch.normal(0, 1, size=(5, 7, 3))
     u = torch.rand([5])
     assert torch.equal(full, x0 * 2 + u[:, None, None])
+
+
+def _screen_worker(rank, ws, port, q):
+    from physdock_b200.sharding import screen_library, shard_ligands
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=ws)
+    seen = []
+
+    def sample_ligand(i):                    # stand-in for trunk + sample_diffusion of ligand i (8 poses, ragged atom counts)
+        seen.append(i)
+        g = torch.Generator().manual_seed(1000 + i)
+        return torch.randn(8, 20 + i, 3, generator=g)
+
+    out = screen_library(7, sample_ligand)
+    assert seen == shard_ligands(7, rank, ws)
+    if rank == 0:
+        q.put(out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_screening_covers_library_in_order():
+    """BASELINE.json configs[3] (screening, ligands sharded round-robin, 8 samples per ligand stay on one rank)."""
+    from physdock_b200.sharding import shard_ligands
+    assert shard_ligands(7, 0, 2) == [0, 2, 4, 6] and shard_ligands(7, 1, 2) == [1, 3, 5]
+    assert sorted(sum((shard_ligands(1000, r, 8) for r in range(8)), [])) == list(range(1000))
+    ws, port = 2, 29573
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_screen_worker, args=(r, ws, port, q)) for r in range(ws)]
+    for p in procs:
+        p.start()
+    out = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert len(out) == 7
+    for i, x in enumerate(out):
+        g = torch.Generator().manual_seed(1000 + i)
+        assert torch.equal(x, torch.randn(8, 20 + i, 3, generator=g))
