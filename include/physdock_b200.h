@@ -165,6 +165,11 @@ int pdk_op_gemm_gate_resid(const void* Ah, const void* Al, int64_t lda, const vo
 int pdk_op_gemm_swiglu(const void* Ah, const void* Al, int64_t lda, const void* Wh, const void* Wl, int64_t ldw,
                        int64_t M, int64_t N, int64_t K, void* ph, void* pl, int64_t ldp, void* stream);
 /* q, k, v: fp16 [B,H,S_pad,64], each row = [hi 32 | lo 32] (the two split planes interleaved: 128-byte rows) */
+/* Fused DiTTransition of the atom stacks (c = 128; transitions.py:21-30): x[M,128] += w2(SiLU(w1 xn) * w3 xn) * gate,
+ * xn = LN(x) * (1 + scale) + shift, (shift | scale | gate) = mod[sample * mod_stride + mod_off ...]. */
+int pdk_op_transition_fused(float* x, const float* mod, int64_t mod_stride, int64_t mod_off, const void* w13h,
+                            const void* w13l, const void* w2h, const void* w2l, int64_t M, int64_t hidden,
+                            int64_t rows_per_sample, float eps, void* stream);
 int pdk_op_gemm_qkv(const void* Ah, const void* Al, int64_t lda, const void* Wh, const void* Wl, int64_t ldw,
                     int64_t M, int64_t c, const float* norm_q, const float* norm_k, float rms_eps, float q_scale,
                     int64_t rows_per_sample, void* q, void* k, void* v, void* stream);

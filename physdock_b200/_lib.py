@@ -72,6 +72,7 @@ PROTOTYPES = {
     "pdk_op_gemm_gate_resid": (_int, [_vp, _vp, _i64, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _i64, _i64,
                                       _vp, _i64, _vp]),
     "pdk_op_gemm_swiglu": (_int, [_vp, _vp, _i64, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _i64, _vp]),
+    "pdk_op_transition_fused": (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _f32, _vp]),
     "pdk_op_gemm_qkv": (_int, [_vp, _vp, _i64, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _f32, _f32, _i64] +
                         [_vp] * 3 + [_vp]),
     "pdk_op_attention": (_int, [_vp] * 6 + [_i64, _i64, _i64, _vp]),

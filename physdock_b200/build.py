@@ -9,7 +9,7 @@ import sys
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB_NAME = "libphysdock_b200.so"
 LIB_PATH = os.path.join(CSRC, LIB_NAME)
-SOURCES = ["gemm_umma.cu", "tmap.cu", "attention_umma.cu", "pairbias.cu", "glue.cu", "coords.cu", "physics.cu", "capi.cu"]
+SOURCES = ["gemm_umma.cu", "transition_umma.cu", "tmap.cu", "attention_umma.cu", "pairbias.cu", "glue.cu", "coords.cu", "physics.cu", "capi.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

@@ -97,6 +97,11 @@ Workspace carve(const pdk_dit& h, int64_t B, int64_t Sa, int64_t St, uint8_t* ba
 }
 
 constexpr int kLaunchesPerBlock = 7;
+constexpr int kLaunchesPerFusedBlock = 5;        // atom blocks: the transition is one kernel (transition_umma.cu)
+inline bool fused_transition_enabled() {
+    static const bool on = getenv("PDK_NO_FUSED_TRANSITION") == nullptr;      // measurement switch
+    return on;
+}
 
 // One DiTBlock (transformers.py:155-159): x += Attn(x); x += Transition(x).
 int run_block(const pdk_dit& h, const pdk_block_weights& bw, const Workspace& ws, float* x, int64_t B, int64_t Sp,
@@ -125,6 +130,14 @@ int run_block(const pdk_dit& h, const pdk_block_weights& bw, const Workspace& ws
     g.gate = ws.mod + bw.mod_attn_off + 2 * c; g.gate_stride = nmod; g.rows_per_sample = (int)Sp;
     PDK_TRY("gemm(out)", launch_gemm(EPI_GATE_RESID, g, st));
     // --- transition (transitions.py:21-30)
+    if (c == 128 && fused_transition_enabled()) {
+        TransitionArgs ta{};
+        ta.x = x; ta.mod = ws.mod; ta.mod_stride = nmod; ta.mod_off = (int)bw.mod_ffn_off;
+        ta.w13h = H(bw.w13_h); ta.w13l = H(bw.w13_l); ta.w2h = H(bw.w2_h); ta.w2l = H(bw.w2_l);
+        ta.M = M; ta.hidden = hidden; ta.rows_per_sample = (int)Sp; ta.eps = eps;
+        PDK_TRY("transition(fused)", launch_transition_fused(ta, st));
+        return 0;
+    }
     PDK_TRY("adaln(ffn)", launch_adaln(x, ws.mod, nmod, (int)bw.mod_ffn_off, ws.xh, ws.xl, (int)B, (int)Sp, c, eps, st));
     g = GemmArgs{};
     g.Ah = ws.xh; g.Al = ws.xl; g.lda = c;
@@ -225,7 +238,8 @@ int pdk_dit_prepare_complex(pdk_dit* h, const float* a, const float* ap, const f
 int64_t pdk_dit_launches_per_denoise(const pdk_dit* h) {
     if (!h) return 0;
     // time_embed, mod, precond | blocks | split, gemm(down), segmean | split, gemm(up), gather | denoise_out
-    return 3 + kLaunchesPerBlock * (2 * h->d.n_atom_blocks + h->d.n_token_blocks) + 3 + 3 + 1;
+    const int64_t per_atom_block = fused_transition_enabled() ? kLaunchesPerFusedBlock : kLaunchesPerBlock;
+    return 3 + per_atom_block * 2 * h->d.n_atom_blocks + kLaunchesPerBlock * h->d.n_token_blocks + 3 + 3 + 1;
 }
 
 int pdk_dit_denoise(pdk_dit* h, const float* x_hat, const float* t_hat, int64_t B, void* workspace,
@@ -419,6 +433,17 @@ int pdk_op_gemm_swiglu(const void* Ah, const void* Al, int64_t lda, const void* 
     GemmArgs g = base_args(Ah, Al, lda, Wh, Wl, ldw, M, N, K);
     g.ph = H(ph); g.pl = H(pl); g.ldp = (int)ldp;
     PDK_TRY("gemm_swiglu", launch_gemm(EPI_SWIGLU, g, S(stream)));
+    return 0;
+}
+int pdk_op_transition_fused(float* x, const float* mod, int64_t mod_stride, int64_t mod_off, const void* w13h,
+                            const void* w13l, const void* w2h, const void* w2l, int64_t M, int64_t hidden,
+                            int64_t rows_per_sample, float eps, void* stream) {
+    if (!x || !mod || !w13h || !w13l || !w2h || !w2l) return fail_msg("pdk_op_transition_fused", "null argument");
+    TransitionArgs ta{};
+    ta.x = x; ta.mod = mod; ta.mod_stride = (int)mod_stride; ta.mod_off = (int)mod_off;
+    ta.w13h = H(w13h); ta.w13l = H(w13l); ta.w2h = H(w2h); ta.w2l = H(w2l);
+    ta.M = (int)M; ta.hidden = (int)hidden; ta.rows_per_sample = (int)rows_per_sample; ta.eps = eps;
+    PDK_TRY("transition_fused", launch_transition_fused(ta, S(stream)));
     return 0;
 }
 int pdk_op_gemm_qkv(const void* Ah, const void* Al, int64_t lda, const void* Wh, const void* Wl, int64_t ldw, int64_t M,

@@ -34,6 +34,18 @@ struct GemmArgs {
 };
 cudaError_t launch_gemm(GemmEpilogue epi, const GemmArgs& a, cudaStream_t st);
 
+// ----------------------------------------------------------------------------- fused transition (transition_umma.cu), c = 128
+// x[M,128] += w2( SiLU(w1 xn) * (w3 xn) ) * gate, xn = LN(x) * (1 + scale) + shift; (shift, scale, gate) = mod[sample, off..off+3c)
+struct TransitionArgs {
+    float* x;                       // [M,128] fp32, updated in place
+    const float* mod; int mod_stride; int mod_off;
+    const __half* w13h; const __half* w13l;     // [2*hidden,128], rows interleaved (16 x w1 | 16 x w3)
+    const __half* w2h; const __half* w2l;       // [128,hidden]
+    int M, hidden, rows_per_sample;
+    float eps;
+};
+cudaError_t launch_transition_fused(const TransitionArgs& a, cudaStream_t st);
+
 // ----------------------------------------------------------------------------- pair-bias attention
 // q,k,v [B,H,S_pad,64] with rows [hi 32 | lo 32] (q pre-scaled by log2e/sqrt(32)); bias [H,S_pad,S_pad] fp32
 // (pre-scaled by log2e, pad columns = kPadBias); output planes o[B*S_pad, c] with column h*32+d.

@@ -1,0 +1,320 @@
+// Fused DiTTransition for the atom stacks (c = 128): ONE kernel for
+//     x += w2( SiLU(w1 xn) * (w3 xn) ) * gate,   xn = LN_noaffine(x) * (1 + scale) + shift
+// (reference PhysDock/models/layers/transitions.py:21-30, feed_forward.py:30-31, adaptive_layer_norm_zero.py:19-21),
+// replacing the three launches adaln_kernel<128> -> gemm_umma_kernel<SWIGLU> -> gemm_umma_kernel<GATE_RESID> and the two
+// HBM round trips between them (x-tilde planes 16.8 MB, hidden planes 50 MB per launch at B=16, Na=2048).
+//
+// CTA = 128 rows of x (persistent over row tiles).  Per tile:
+//   LN warps    : read the fp32 rows, LayerNorm + modulation, split to fp16 hi/lo and write the A operand straight into
+//                 shared memory in the SWIZZLE_128B K-major layout tcgen05 expects (64 KB, stays for all of GEMM 1)
+//   GEMM 1      : for each block j of 64 hidden units: acc1[j&1] (TMEM, 128 columns) = xn W13_j^T, W13 rows interleaved
+//                 (16 x w1 | 16 x w3) so one 32-column chunk holds both factors of 16 hidden units
+//   epilogue j  : SiLU(h1) * h3 on the accumulator rows, split, written to shared memory as the K-major A operand of
+//   GEMM 2      : acc2 (TMEM) += H_j W2[:, 64j:64j+64]^T        -- the hidden activations never leave the SM
+//   final       : x += acc2 * gate  (row-contiguous stores through a smem staging tile, residual prefetched)
+// Warps: 0 = TMA producer (weights only: starts before the previous kernel has finished, PDL), 1 = MMA issuer,
+// 2-17 = LN / epilogue warps (thread = one row x one 32-column chunk).  The weight tiles stream through a 3-stage ring
+// in exactly the order the MMA warp consumes them (G1_0, G1_1, G2_0, G1_2, G2_1, ...).
+#include "common.cuh"
+#include "kernels.h"
+#include "umma.cuh"
+
+namespace pdk {
+
+namespace {
+
+constexpr int TM = 128, TC = 128, TK = 64;
+constexpr int PT = TM * TK * 2;                 // 16 KB: one fp16 plane tile [128 rows][64 halves], 128-byte rows
+constexpr int OFF_A = 0;                        // hi k0 | hi k1 | lo k0 | lo k1
+constexpr int OFF_H = 4 * PT;                   // two buffers of (hi | lo)
+constexpr int OFF_W = OFF_H + 4 * PT;           // 3 stages of (hi | lo)
+constexpr int W_STAGES = 3;
+constexpr int T_SMEM = OFF_W + W_STAGES * 2 * PT + 1024;
+constexpr int T_EPI_WARPS = 16;
+constexpr int T_THREADS = (2 + T_EPI_WARPS) * 32;
+constexpr int STG_ROW = 48, STG_WARP = 32 * STG_ROW;        // final-epilogue staging (inside the H region)
+constexpr uint32_t COL_ACC1 = 0, COL_ACC2 = 256;
+
+struct TBars {
+    uint64_t w_full[W_STAGES], w_empty[W_STAGES];
+    uint64_t a_ready;
+    uint64_t acc1_full[2], acc1_empty[2], h_full[2], h_empty[2];
+    uint64_t acc2_full, acc2_empty;
+};
+
+PDK_DEV void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+PDK_DEV void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+PDK_DEV float silu_mufu(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + ex2(-kLog2e * x)));
+    return x * r;
+}
+
+__global__ void __launch_bounds__(T_THREADS, 1)
+transition_umma_kernel(const __grid_constant__ CUtensorMap mW13h, const __grid_constant__ CUtensorMap mW13l,
+                       const __grid_constant__ CUtensorMap mW2h, const __grid_constant__ CUtensorMap mW2l,
+                       const TransitionArgs p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) TBars bars;
+    __shared__ uint32_t tmem_slot;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t sm = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int NT = p.hidden / TK;                       // blocks of 64 hidden units
+    const int num_tiles = p.M / TM;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < W_STAGES; ++s) { mbar_init(smem_u32(&bars.w_full[s]), 1); mbar_init(smem_u32(&bars.w_empty[s]), 1); }
+        mbar_init(smem_u32(&bars.a_ready), T_EPI_WARPS);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(smem_u32(&bars.acc1_full[b]), 1);
+            mbar_init(smem_u32(&bars.acc1_empty[b]), T_EPI_WARPS);
+            mbar_init(smem_u32(&bars.h_full[b]), T_EPI_WARPS);
+            mbar_init(smem_u32(&bars.h_empty[b]), 1);
+        }
+        mbar_init(smem_u32(&bars.acc2_full), 1);
+        mbar_init(smem_u32(&bars.acc2_empty), T_EPI_WARPS);
+        mbar_fence_init();
+        tma_prefetch_desc(&mW13h); tma_prefetch_desc(&mW13l); tma_prefetch_desc(&mW2h); tma_prefetch_desc(&mW2l);
+    }
+    griddep_launch();
+    if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+
+    if (warp == 0) {
+        // ================================================================= TMA producer (weights only; no griddep_wait)
+        int s = 0;
+        uint32_t ph = 0;
+        auto load = [&](const CUtensorMap* mh, const CUtensorMap* ml, int c0, int c1) {
+            mbar_wait(smem_u32(&bars.w_empty[s]), ph ^ 1u);
+            if (elect_one()) {
+                const uint32_t bar = smem_u32(&bars.w_full[s]);
+                const uint32_t dst = sm + OFF_W + s * 2 * PT;
+                mbar_expect_tx(bar, 2 * PT);
+                tma_load_2d(dst, mh, bar, c0, c1);
+                tma_load_2d(dst + PT, ml, bar, c0, c1);
+            }
+            __syncwarp();
+            if (++s == W_STAGES) { s = 0; ph ^= 1u; }
+        };
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            for (int j = 0; j <= NT; ++j) {
+                if (j < NT) {
+                    load(&mW13h, &mW13l, 0, j * 128);
+                    load(&mW13h, &mW13l, TK, j * 128);
+                }
+                if (j >= 1) load(&mW2h, &mW2l, (j - 1) * TK, 0);
+            }
+        }
+    } else if (warp == 1) {
+        // ================================================================= MMA issuer
+        constexpr uint32_t idesc = umma_idesc_f16(TM, TC);
+        int s = 0;
+        uint32_t ph = 0;
+        uint32_t g1 = 0, g2 = 0;        // global counters of GEMM-1 / GEMM-2 blocks (buffer = g & 1, use index = g >> 1)
+        int it = 0;
+        auto mma_stage = [&](uint32_t a_hi, uint32_t a_lo, uint32_t d, bool first) {      // one [128 x 64] K tile, 12 MMAs
+            mbar_wait(smem_u32(&bars.w_full[s]), ph);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t w = sm + OFF_W + s * 2 * PT;
+                const uint64_t ah = smem_desc(a_hi, 1024, kLayoutSw128), al = smem_desc(a_lo, 1024, kLayoutSw128);
+                const uint64_t wh = smem_desc(w, 1024, kLayoutSw128), wl = smem_desc(w + PT, 1024, kLayoutSw128);
+#pragma unroll
+                for (int ks = 0; ks < TK / 16; ++ks) {
+                    const uint64_t o = (uint64_t)(ks * 2);
+                    umma_f16(d, al + o, wh + o, idesc, (first && ks == 0) ? 0u : 1u);
+                    umma_f16(d, ah + o, wl + o, idesc, 1u);
+                    umma_f16(d, ah + o, wh + o, idesc, 1u);
+                }
+                umma_commit(smem_u32(&bars.w_empty[s]));
+            }
+            __syncwarp();
+            if (++s == W_STAGES) { s = 0; ph ^= 1u; }
+        };
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+            mbar_wait(smem_u32(&bars.a_ready), (uint32_t)it & 1u);
+            for (int j = 0; j <= NT; ++j) {
+                if (j < NT) {
+                    const uint32_t b = g1 & 1u;
+                    mbar_wait(smem_u32(&bars.acc1_empty[b]), ((g1 >> 1) & 1u) ^ 1u);
+                    tc_fence_after();
+                    const uint32_t d = tmem + COL_ACC1 + b * TC;
+                    mma_stage(sm + OFF_A, sm + OFF_A + 2 * PT, d, true);
+                    mma_stage(sm + OFF_A + PT, sm + OFF_A + 3 * PT, d, false);
+                    if (elect_one()) umma_commit(smem_u32(&bars.acc1_full[b]));
+                    __syncwarp();
+                    ++g1;
+                }
+                if (j >= 1) {
+                    const uint32_t b = g2 & 1u;
+                    if (j == 1) {                     // acc2 of the previous tile has been drained
+                        mbar_wait(smem_u32(&bars.acc2_empty), ((uint32_t)it & 1u) ^ 1u);
+                    }
+                    mbar_wait(smem_u32(&bars.h_full[b]), (g2 >> 1) & 1u);
+                    tc_fence_after();
+                    const uint32_t hb = sm + OFF_H + b * 2 * PT;
+                    mma_stage(hb, hb + PT, tmem + COL_ACC2, j == 1);
+                    if (elect_one()) {
+                        umma_commit(smem_u32(&bars.h_empty[b]));
+                        if (j == NT) umma_commit(smem_u32(&bars.acc2_full));
+                    }
+                    __syncwarp();
+                    ++g2;
+                }
+            }
+        }
+    } else {
+        // ================================================================= LN / epilogue warps
+        griddep_wait();                               // x and mod come from the preceding kernels
+        const int ew = warp - 2;
+        const int q = warp & 3;                       // TMEM lane quarter
+        const int ch = ew >> 2;                       // 32-column chunk of a 128-column accumulator
+        const int r = q * 32 + lane;                  // accumulator row of this thread
+        const uint32_t stg = sm + OFF_H + ew * STG_WARP;
+        const int rr = lane >> 1, rc = lane & 1;
+        // LayerNorm + modulation of 8 rows per warp -> A planes (SWIZZLE_128B, K-major)
+        auto layer_norm_tile = [&](int t) {
+            const int m0 = t * TM;
+            const float* shift = p.mod + (size_t)(m0 / p.rows_per_sample) * p.mod_stride + p.mod_off;
+            const float4 sh = *reinterpret_cast<const float4*>(shift + lane * 4);
+            const float4 sc = *reinterpret_cast<const float4*>(shift + TC + lane * 4);
+            float4 v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = *reinterpret_cast<const float4*>(p.x + (size_t)(m0 + ew * 8 + i) * TC + lane * 4);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int row = ew * 8 + i;
+                const float mean = warp_sum(v[i].x + v[i].y + v[i].z + v[i].w) * (1.f / TC);
+                v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+                const float rstd = 1.0f / sqrtf(warp_sum(v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w) * (1.f / TC) + p.eps);
+                uint2 hi, lo;
+                split2(v[i].x * rstd * (1.f + sc.x) + sh.x, v[i].y * rstd * (1.f + sc.y) + sh.y, hi.x, lo.x);
+                split2(v[i].z * rstd * (1.f + sc.z) + sh.z, v[i].w * rstd * (1.f + sc.w) + sh.w, hi.y, lo.y);
+                // columns lane*4 .. +3: K tile lane/16, 16-byte chunk (lane%16)/2 (XOR row&7), 8-byte half lane&1
+                const uint32_t off = (uint32_t)((lane >> 4) * PT + row * 128 + (((((lane & 15) >> 1)) ^ (row & 7)) << 4) + (lane & 1) * 8);
+                asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(sm + OFF_A + off), "r"(hi.x), "r"(hi.y) : "memory");
+                asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(sm + OFF_A + 2 * PT + off), "r"(lo.x), "r"(lo.y) : "memory");
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bars.a_ready));
+        };
+        uint32_t g = 0;                               // global hidden-block counter (matches g1 / g2 of the MMA warp)
+        int it = 0;
+        if ((int)blockIdx.x < num_tiles) layer_norm_tile(blockIdx.x);
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+            const int m0 = t * TM;
+            const int row0 = m0 + q * 32;
+            const int col = ch * 32;
+            // ---- hidden blocks: SiLU(h1) * h3 -> H planes
+            for (int j = 0; j < NT; ++j, ++g) {
+                const uint32_t b = g & 1u;
+                mbar_wait(smem_u32(&bars.acc1_full[b]), (g >> 1) & 1u);
+                tc_fence_after();
+                uint32_t raw[32];
+                tmem_ld32(tmem + COL_ACC1 + b * TC + ((uint32_t)(q * 32) << 16) + ch * 32, raw);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&bars.acc1_empty[b]));
+                uint32_t w[16];     // words 0-7: hi halves of this chunk's 16 hidden values, 8-15: lo halves
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    split2(silu_mufu(__uint_as_float(raw[2 * i])) * __uint_as_float(raw[16 + 2 * i]),
+                           silu_mufu(__uint_as_float(raw[2 * i + 1])) * __uint_as_float(raw[16 + 2 * i + 1]), w[i], w[8 + i]);
+                mbar_wait(smem_u32(&bars.h_empty[b]), ((g >> 1) & 1u) ^ 1u);      // GEMM 2 has consumed the previous content
+                const uint32_t hb = sm + OFF_H + b * 2 * PT + r * 128;
+                const uint32_t c0 = (uint32_t)(((2 * ch) ^ (r & 7)) << 4), c1 = (uint32_t)(((2 * ch + 1) ^ (r & 7)) << 4);
+                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(hb + c0), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(hb + c1), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(hb + PT + c0), "r"(w[8]), "r"(w[9]), "r"(w[10]), "r"(w[11]) : "memory");
+                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(hb + PT + c1), "r"(w[12]), "r"(w[13]), "r"(w[14]), "r"(w[15]) : "memory");
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&bars.h_full[b]));
+            }
+            // ---- residual tile of the final epilogue (fetched while GEMM 2 finishes)
+            float4 xres[8];
+#pragma unroll
+            for (int ps = 0; ps < 4; ++ps)
+#pragma unroll
+                for (int k = 0; k < 2; ++k)
+                    xres[ps * 2 + k] = *reinterpret_cast<const float4*>(p.x + (size_t)(row0 + k * 16 + rr) * TC + col + ps * 8 + rc * 4);
+            // ---- A operand of the NEXT tile (all GEMM-1 MMAs of this tile have completed: acc1_full of its last block)
+            if (t + (int)gridDim.x < num_tiles) layer_norm_tile(t + gridDim.x);
+            // ---- final epilogue: x += acc2 * gate
+            mbar_wait(smem_u32(&bars.acc2_full), (uint32_t)it & 1u);
+            tc_fence_after();
+            uint32_t raw[32];
+            tmem_ld32(tmem + COL_ACC2 + ((uint32_t)(q * 32) << 16) + ch * 32, raw);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bars.acc2_empty));
+            const float* gate = p.mod + (size_t)(m0 / p.rows_per_sample) * p.mod_stride + p.mod_off + 2 * TC + col;
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float4 g4 = __ldg(reinterpret_cast<const float4*>(gate) + i);
+                v[4 * i] = __uint_as_float(raw[4 * i]) * g4.x; v[4 * i + 1] = __uint_as_float(raw[4 * i + 1]) * g4.y;
+                v[4 * i + 2] = __uint_as_float(raw[4 * i + 2]) * g4.z; v[4 * i + 3] = __uint_as_float(raw[4 * i + 3]) * g4.w;
+            }
+#pragma unroll
+            for (int ps = 0; ps < 4; ++ps) {
+                __syncwarp();
+                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(stg + lane * STG_ROW), "r"(__float_as_uint(v[ps * 8])),
+                             "r"(__float_as_uint(v[ps * 8 + 1])), "r"(__float_as_uint(v[ps * 8 + 2])), "r"(__float_as_uint(v[ps * 8 + 3])) : "memory");
+                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(stg + lane * STG_ROW + 16), "r"(__float_as_uint(v[ps * 8 + 4])),
+                             "r"(__float_as_uint(v[ps * 8 + 5])), "r"(__float_as_uint(v[ps * 8 + 6])), "r"(__float_as_uint(v[ps * 8 + 7])) : "memory");
+                __syncwarp();
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    float4 o;
+                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w)
+                                 : "r"(stg + (k * 16 + rr) * STG_ROW + rc * 16));
+                    const float4 xr = xres[ps * 2 + k];
+                    o.x += xr.x; o.y += xr.y; o.z += xr.z; o.w += xr.w;
+                    *reinterpret_cast<float4*>(p.x + (size_t)(row0 + k * 16 + rr) * TC + col + ps * 8 + rc * 4) = o;
+                }
+            }
+            // the staging tiles live inside the H buffers: nobody may write the next tile's H before all warps are done
+            named_bar_sync(1, T_EPI_WARPS * 32);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+}  // namespace
+
+cudaError_t launch_transition_fused(const TransitionArgs& a, cudaStream_t st) {
+    if (a.M <= 0 || a.M % TM || a.hidden <= 0 || a.hidden % TK || a.rows_per_sample <= 0 || a.rows_per_sample % TM)
+        return cudaErrorInvalidValue;
+    if ((a.mod_off % 4) || (a.mod_stride % 4)) return cudaErrorInvalidValue;
+    static bool configured = false;
+    static int num_sms = 0;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(transition_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM);
+        if (e != cudaSuccess) return e;
+        int dev = 0;
+        if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+        if ((e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+        configured = true;
+    }
+    CUtensorMap m13h, m13l, m2h, m2l;
+    cudaError_t e;
+    if ((e = get_tensor_map_f16(a.w13h, 2 * a.hidden, TC, TC, 128, TK, 128, &m13h)) != cudaSuccess) return e;
+    if ((e = get_tensor_map_f16(a.w13l, 2 * a.hidden, TC, TC, 128, TK, 128, &m13l)) != cudaSuccess) return e;
+    if ((e = get_tensor_map_f16(a.w2h, TC, a.hidden, a.hidden, 128, TK, 128, &m2h)) != cudaSuccess) return e;
+    if ((e = get_tensor_map_f16(a.w2l, TC, a.hidden, a.hidden, 128, TK, 128, &m2l)) != cudaSuccess) return e;
+    const int tiles = a.M / TM;
+    const int grid = tiles < num_sms ? tiles : num_sms;
+    PDK_LAUNCH_CHECK(launch_pdl(transition_umma_kernel, dim3(grid), dim3(T_THREADS), (size_t)T_SMEM, st, m13h, m13l, m2h, m2l, a));
+    return cudaGetLastError();
+}
+
+}  // namespace pdk

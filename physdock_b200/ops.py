@@ -108,6 +108,18 @@ def gemm_swiglu(ah, al, w13h, w13l):
     return ph, pl
 
 
+def transition_fused(x: torch.Tensor, mod: torch.Tensor, mod_off: int, w13h, w13l, w2h, w2l, rows_per_sample: int,
+                     eps: float) -> torch.Tensor:
+    """In place on x [M,128] fp32: the whole atom DiTTransition (AdaLN + SwiGLU + w2 + gate + residual) in one kernel."""
+    lib = _lib.load()
+    M, c = x.shape
+    hidden = w2h.shape[1]
+    _lib.check(lib.pdk_op_transition_fused(_lib.ptr(x), _lib.ptr(mod), mod.shape[1], mod_off, _lib.ptr(w13h), _lib.ptr(w13l),
+                                           _lib.ptr(w2h), _lib.ptr(w2l), M, hidden, rows_per_sample, eps,
+                                           _lib.stream_ptr(x.device)), "transition_fused")
+    return x
+
+
 def interleave_planes(x: torch.Tensor) -> torch.Tensor:
     """fp32 [..., 32] -> fp16 [..., 64] with rows [hi 32 | lo 32] (the q/k/v operand layout of the attention kernel)."""
     hi, lo = split_planes(x)

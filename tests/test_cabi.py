@@ -46,7 +46,7 @@ def test_handle_lifecycle_and_sizes_without_gpu(lib):
     assert ab.value == 6 * 4 * 2048 * 2048 * 4 and tb.value == 12 * 16 * 256 * 256 * 4     # 403 MB + 50 MB
     assert lib.pdk_dit_workspace_bytes(h, 16, 2048, 256, C.byref(ws)) == 0
     assert 100e6 < ws.value < 2e9
-    assert lib.pdk_dit_launches_per_denoise(h) == 3 + 7 * 18 + 7
+    assert lib.pdk_dit_launches_per_denoise(h) == 3 + 5 * 6 + 7 * 12 + 7     # atom transition fused
     # errors are reported, not swallowed
     assert lib.pdk_dit_denoise(h, None, None, 1, None, 0, None, None) != 0
     assert b"no prepared complex" in lib.pdk_last_error()

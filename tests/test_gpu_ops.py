@@ -189,6 +189,39 @@ def test_transition_block(env, bi, xk, outk, S):
     rel_close(outk, got, k[outk], rtol=0, atol=1e-5 * float(k[outk].abs().max()))
 
 
+def test_fused_atom_transition_vs_oracle_and_unfused(env):
+    """transition_umma.cu (one kernel) against the oracle KAT and against the three-kernel path it replaces."""
+    from physdock_b200 import ops
+    dims, sd, dit, k = env
+    P = dit._packed
+    bi, x = ATOM_BI, k["ba"]
+    B, _, c = x.shape
+    mod = ops.mod_gemv(F.silu(k["t_emb"]), P["wmod"], P["bmod"])
+    off = int(dit._block_array[bi].mod_ffn_off)
+    xp = pad_rows(x, 128).contiguous()                       # [B,128,c]; the fused kernel works in place on the residual
+    fused = xp.clone().view(-1, c)
+    ops.transition_fused(fused, mod, off, P[f"b{bi}.w13_h"], P[f"b{bi}.w13_l"], P[f"b{bi}.w2_h"], P[f"b{bi}.w2_l"], 128, dims.eps)
+    hi, lo = ops.adaln(xp, mod, off, dims.eps)
+    hh, hl = ops.gemm_swiglu(hi.view(-1, c), lo.view(-1, c), P[f"b{bi}.w13_h"], P[f"b{bi}.w13_l"])
+    ref = xp.clone().view(-1, c)
+    ops.gemm_gate_resid(hh, hl, P[f"b{bi}.w2_h"], P[f"b{bi}.w2_l"], None, mod[:, off + 2 * c:], mod.shape[1], 128, ref)
+    want = x + k["atom_trans_out"]                            # the KAT holds the transition's delta
+    S = want.shape[1]
+    rel_close("fused transition vs oracle", fused.view(B, 128, c)[:, :S], want, rtol=0, atol=1e-5 * float(want.abs().max()))
+    rel_close("fused transition vs unfused kernels", fused, ref, rtol=0, atol=2e-6 * float(ref.abs().max()))
+    # several row tiles per CTA (persistent loop, both TMEM/H buffers, A operand rebuilt per tile): 300 tiles on 148 SMs
+    g = torch.Generator(device=DEV).manual_seed(5)
+    big = torch.randn(300 * 128, c, generator=g, device=DEV)
+    modb = torch.randn(300, mod.shape[1], generator=g, device=DEV) * 0.3
+    a = big.clone()
+    ops.transition_fused(a, modb, off, P[f"b{bi}.w13_h"], P[f"b{bi}.w13_l"], P[f"b{bi}.w2_h"], P[f"b{bi}.w2_l"], 128, dims.eps)
+    hi, lo = ops.adaln(big.view(300, 128, c), modb, off, dims.eps)
+    hh, hl = ops.gemm_swiglu(hi.view(-1, c), lo.view(-1, c), P[f"b{bi}.w13_h"], P[f"b{bi}.w13_l"])
+    b = big.clone()
+    ops.gemm_gate_resid(hh, hl, P[f"b{bi}.w2_h"], P[f"b{bi}.w2_l"], None, modb[:, off + 2 * c:], modb.shape[1], 128, b)
+    rel_close("fused transition, 300 tiles", a, b, rtol=0, atol=2e-6 * float(b.abs().max()))
+
+
 # ------------------------------------------------------------------------------------- glue
 def test_precond_downscale_upscale_denoise(env):
     from physdock_b200 import ops
