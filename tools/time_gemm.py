@@ -29,6 +29,8 @@ shapes = {
   "atom store  32768x512x128": lambda: ops.gemm_store(*xa, *W["adown"]),
   "atom qkv    32768x384x128": lambda: ops.gemm_qkv(*xa, *W["aqkv"], nq, nk, 1e-8, 16, 2048),
   "atom out    32768x128x128": lambda: ops.gemm_gate_resid(*xa, *W["ao"], None, gate_a, 128, 2048, out_a),
+  "atom fused transition    ": lambda: ops.transition_fused(out_a, mod_a, 0, *W["a13"], *W["a2"], 2048, 1e-8),
+  "atom adaln               ": lambda: ops.adaln(out_a.view(16, 2048, 128), mod_a, 0, 1e-8),
   "tok  qkv    4096x1536x512": lambda: ops.gemm_qkv(*xt, *W["tqkv"], nq, nk, 1e-8, 16, 256),
   "tok  swiglu 4096x2816x512": lambda: ops.gemm_swiglu(*xt, *W["t13"]),
   "tok  w2     4096x512x1408": lambda: ops.gemm_gate_resid(*ht, *W["t2"], None, gate_t, 512, 256, out_t),
@@ -39,6 +41,7 @@ W = {"a13": planes(768, 128), "a2": planes(128, 384), "adown": planes(512, 128),
 nq, nk = torch.ones(32, device=dev), torch.ones(32, device=dev)
 gate_a, gate_t = torch.randn(16, 128, device=dev), torch.randn(16, 512, device=dev)
 out_a, out_t = torch.zeros(Ma, 128, device=dev), torch.zeros(Mt, 512, device=dev)
+mod_a = torch.randn(16, 384, device=dev) * 0.1
 print(os.environ.get("PHYSDOCK_B200_LIB", "product build"))
 for k, fn in shapes.items():
     print(f"  {k}: {timeit(fn):7.1f} us")
