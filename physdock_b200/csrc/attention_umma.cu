@@ -8,21 +8,23 @@
 // is TMA-loaded once per key tile and read by all of them from shared memory, which divides the dominant L2
 // stream (bias, 4 B per score) by the group size.  Work unit u = (key tile j of 64 keys, sample g).
 //
-//   warp 8  TMA producer   : Q of the group (once); per key tile the bias tile [128 x 64] fp32 (two SWIZZLE_128B
+//   warp 16 TMA producer   : Q of the group (once); per key tile the bias tile [128 x 64] fp32 (two SWIZZLE_128B
 //                            boxes, double buffered) and per unit K, V [64 keys x 64 halves] (6-stage ring).  q/k/v
 //                            rows are stored interleaved [hi 32 | lo 32] = 128 bytes because TMA boxes narrower than
 //                            128 B run at less than half rate (tests/cuda/umma_probe.cu test 7); the hi and lo K=16
 //                            slices of a row are then just byte offsets 0/32 and 64/96 into a SWIZZLE_128B tile.
-//   warp 9  QK issuer      : S_g = Q_g K^T   (SS, M128 N64 K16 x 2 slices x 3 split products) into TMEM buffer g
-//   warp 10 PV issuer      : O_g += P_g V    (TS: P from TMEM, V MN-major from smem; 4 slices x 3 products)
+//   warp 17 QK issuer      : S_g = Q_g K^T   (SS, M128 N64 K16 x 2 slices x 3 split products) into TMEM buffer g
+//   warp 18 PV issuer      : O_g += P_g V    (TS: P from TMEM, V MN-major from smem; 4 slices x 3 products)
 //                            Two issuing warps because one warp's serialized waits/commits left the tensor pipe
 //                            idle ~40% of the time (profiles/r01_attention_timeline.txt); QK(j,g) is ordered after
 //                            PV(j-1,g) through the pv_done barrier (S and P share a TMEM buffer).
-//   warps 0-3 / 4-7        : two softmax warpgroups (samples g even / odd).  Thread = one query row: reads its 64
-//                            scores with tcgen05.ld, adds the bias row, row max / exp2 / row sum entirely in
-//                            registers (no shuffles), splits P into fp16 hi/lo and writes it back over S with
-//                            tcgen05.st (S and P alias).  O is rescaled lazily (only when the row max grows by
-//                            more than 2^8), directly in TMEM.
+//   warps 4g .. 4g+3      : softmax warpgroup of sample g (FOUR warpgroups; with two, each serving two samples, the
+//                            softmax warps were busy 87% of the time and set the pace: profiles/r01_attention_timeline.txt).
+//                            Thread = one query row: reads its 64 scores with tcgen05.ld, adds the bias row, row max /
+//                            exp2 / row sum entirely in registers (no shuffles), splits P into fp16 hi/lo and writes it
+//                            back over S with tcgen05.st (S and P alias) in 16-column pieces so that the thread stays
+//                            within 104 registers.  O is rescaled lazily (only when the row max grows by more than
+//                            2^8), directly in TMEM.
 // TMEM: 4 x 64 columns S/P + 4 x 64 columns O (P_hi V_hi + P_lo V_hi | P_hi V_lo, summed in the epilogue).
 #include "common.cuh"
 #include "kernels.h"
@@ -48,7 +50,7 @@ constexpr int OFF_Q = 0;
 constexpr int OFF_BIAS = G * Q_TILE;                 // 64 KB
 constexpr int OFF_KV = OFF_BIAS + 2 * BIAS_TILE;     // 128 KB
 constexpr int SMEM_BYTES = OFF_KV + NS * KV_STAGE + 1024;   // 225 KB
-constexpr int NTHREADS = 352;
+constexpr int NTHREADS = (4 * G + 3) * 32;       // 16 softmax warps + TMA + QK + PV = 608 threads (<= 104 registers each)
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t COL_S = 0, COL_O = 256;
 constexpr float kRescaleThreshold = 8.0f;            // log2 domain: P <= 2^8 stays exact enough in fp16 hi/lo
@@ -71,6 +73,23 @@ PDK_DEV void tmem_st32(uint32_t addr, const uint32_t (&v)[32]) {
           "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]),
           "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]),
           "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31]) : "memory");
+}
+PDK_DEV void tmem_ld16(uint32_t addr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(addr));
+}
+PDK_DEV void tmem_st8(uint32_t addr, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+PDK_DEV void tmem_st16(uint32_t addr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+        ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+          "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
 }
 PDK_DEV void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 PDK_DEV void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
@@ -148,14 +167,14 @@ attention_umma_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_const
         mbar_fence_init();
     }
     griddep_launch();                 // PDL (see common.cuh)
-    if (warp == 9) tmem_alloc(smem_u32(&tmem_slot), TMEM_COLS);
+    if (warp == 4 * G + 1) tmem_alloc(smem_u32(&tmem_slot), TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
     griddep_wait();
 
-    if (warp == 8) {
+    if (warp == 4 * G) {
         // ================================================================= TMA producer
         if (elect_one()) {
             tma_prefetch_desc(&mQ); tma_prefetch_desc(&mK); tma_prefetch_desc(&mV); tma_prefetch_desc(&mBias);
@@ -191,7 +210,7 @@ attention_umma_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_const
                 if (++st == NS) { st = 0; kv_par ^= 1u; }
             }
         }
-    } else if (warp == 9) {
+    } else if (warp == 4 * G + 1) {
         // ================================================================= QK issuer (whole warp loops, one lane issues)
         // S_g(j) = Q_g K_g(j)^T.  The S buffer of sample g doubles as its P buffer, so QK(j,g) waits for PV(j-1,g).
         constexpr uint32_t idesc_qk = umma_idesc_f16(BQ, BKV);          // M128 N64, both K-major
@@ -223,7 +242,7 @@ attention_umma_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_const
                 if (++st == NS) { st = 0; kv_par ^= 1u; }
             }
         }
-    } else if (warp == 10) {
+    } else if (warp == 4 * G + 2) {
         // ================================================================= PV issuer
         // O_g += P_g(j) V_g(j): P from TMEM (written by the softmax threads over S), V MN-major from smem.
         // A V row is [V_hi 32 | V_lo 32], i.e. the MN-major SWIZZLE_128B tile IS the N = 64 operand [V_hi | V_lo]:
@@ -257,131 +276,117 @@ attention_umma_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_const
             }
         }
     } else {
-        // ================================================================= softmax warpgroups
-        const int wg = warp >> 2;
+        // ================================================================= softmax warpgroups (one per sample)
+        const int g = warp >> 2;
         const int row = (warp & 3) * 32 + lane;                 // query row inside the tile == TMEM lane
         const uint32_t tl = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-        float m_run[2] = {0.f, 0.f}, l_run[2] = {0.f, 0.f};
         const uint32_t bias_row = (uint32_t)row * 128u;
         const uint32_t sw = (uint32_t)(row & 7);
-        for (int j = 0; j < NJ; ++j) {
-#pragma unroll
-            for (int gi = 0; gi < 2; ++gi) {
-                const int g = wg + 2 * gi;
-                if (g >= ng) continue;
+        if (g < ng) {
+            float m_run = 0.f, l_run = 0.f;
+            const uint32_t ts = tl + COL_S + g * BKV, to = tl + COL_O + g * 2 * D;
+            for (int j = 0; j < NJ; ++j) {
                 if ((warp & 3) == 0) TRACE(j * ng + g, 3);     // softmax starts waiting for S
                 mbar_wait(smem_u32(&bars.s_full[g]), (uint32_t)j & 1u);
                 if ((warp & 3) == 0) TRACE(j * ng + g, 4);     // S arrived
                 tc_fence_after();
-                uint32_t r0[32], r1[32];
-                tmem_ld32(tl + COL_S + g * BKV, r0);
-                tmem_ld32(tl + COL_S + g * BKV + 32, r1);
-                mbar_wait(smem_u32(&bars.bias_full[j & 1]), ((uint32_t)j >> 1) & 1u);
-                tmem_ld_wait();
                 uint64_t s2[32];                         // the 64 scores of this row as 32 fp32x2 pairs
-                const uint32_t bt = sm + OFF_BIAS + (j & 1) * BIAS_TILE + bias_row;
                 float mx = -INFINITY;
+                const uint32_t bt = sm + OFF_BIAS + (j & 1) * BIAS_TILE + bias_row;
+                mbar_wait(smem_u32(&bars.bias_full[j & 1]), ((uint32_t)j >> 1) & 1u);
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const float4 b4 = lds128(bt + (((uint32_t)c ^ sw) << 4));
-                    s2[2 * c] = add2(pack2(__uint_as_float(r0[4 * c]), __uint_as_float(r0[4 * c + 1])), pack2(b4.x, b4.y));
-                    s2[2 * c + 1] = add2(pack2(__uint_as_float(r0[4 * c + 2]), __uint_as_float(r0[4 * c + 3])), pack2(b4.z, b4.w));
-                    float a0, a1, a2, a3;
-                    unpack2(s2[2 * c], a0, a1);
-                    unpack2(s2[2 * c + 1], a2, a3);
-                    mx = max3(mx, a0, a1);
-                    mx = max3(mx, a2, a3);
-                }
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t r[32];
+                    tmem_ld32(ts + half * 32, r);
+                    tmem_ld_wait();
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const float4 b4 = lds128(bt + BIAS_HALF + (((uint32_t)c ^ sw) << 4));
-                    s2[16 + 2 * c] = add2(pack2(__uint_as_float(r1[4 * c]), __uint_as_float(r1[4 * c + 1])), pack2(b4.x, b4.y));
-                    s2[16 + 2 * c + 1] = add2(pack2(__uint_as_float(r1[4 * c + 2]), __uint_as_float(r1[4 * c + 3])), pack2(b4.z, b4.w));
-                    float a0, a1, a2, a3;
-                    unpack2(s2[16 + 2 * c], a0, a1);
-                    unpack2(s2[16 + 2 * c + 1], a2, a3);
-                    mx = max3(mx, a0, a1);
-                    mx = max3(mx, a2, a3);
+                    for (int c = 0; c < 8; ++c) {
+                        const float4 b4 = lds128(bt + half * BIAS_HALF + (((uint32_t)c ^ sw) << 4));
+                        s2[16 * half + 2 * c] = add2(pack2(__uint_as_float(r[4 * c]), __uint_as_float(r[4 * c + 1])), pack2(b4.x, b4.y));
+                        s2[16 * half + 2 * c + 1] = add2(pack2(__uint_as_float(r[4 * c + 2]), __uint_as_float(r[4 * c + 3])), pack2(b4.z, b4.w));
+                        float a0, a1, a2, a3;
+                        unpack2(s2[16 * half + 2 * c], a0, a1);
+                        unpack2(s2[16 * half + 2 * c + 1], a2, a3);
+                        mx = max3(mx, a0, a1);
+                        mx = max3(mx, a2, a3);
+                    }
                 }
                 mbar_arrive(smem_u32(&bars.bias_empty[j & 1]));
                 if ((warp & 3) == 0) TRACE(j * ng + g, 5);     // S + bias in registers, row max known
                 // ---- running max with lazy rescale of O (in TMEM)
                 if (j == 0) {
-                    m_run[gi] = mx;
+                    m_run = mx;
                 } else {
                     mbar_wait(smem_u32(&bars.pv_done[g]), (uint32_t)(j - 1) & 1u);     // O_g is stable
-                    const bool need = mx > m_run[gi] + kRescaleThreshold;
+                    const bool need = mx > m_run + kRescaleThreshold;
                     if (__any_sync(0xffffffffu, need)) {
                         tc_fence_after();
-                        const float c = need ? ex2(m_run[gi] - mx) : 1.0f;
-                        if (need) m_run[gi] = mx;
-                        l_run[gi] *= c;
-                        uint32_t o[32], o2[32];
-                        tmem_ld32(tl + COL_O + g * 2 * D, o);
-                        tmem_ld32(tl + COL_O + g * 2 * D + 32, o2);
-                        tmem_ld_wait();
+                        const float c = need ? ex2(m_run - mx) : 1.0f;
+                        if (need) m_run = mx;
+                        l_run *= c;
+#pragma unroll 1
+                        for (int q4 = 0; q4 < 4; ++q4) {       // 16 columns at a time: rare path, keep it out of the register budget
+                            uint32_t o[16];
+                            tmem_ld16(to + q4 * 16, o);
+                            tmem_ld_wait();
 #pragma unroll
-                        for (int k = 0; k < 32; ++k) {
-                            o[k] = __float_as_uint(__uint_as_float(o[k]) * c);
-                            o2[k] = __float_as_uint(__uint_as_float(o2[k]) * c);
+                            for (int k = 0; k < 16; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * c);
+                            tmem_st16(to + q4 * 16, o);
                         }
-                        tmem_st32(tl + COL_O + g * 2 * D, o);
-                        tmem_st32(tl + COL_O + g * 2 * D + 32, o2);
                     }
                 }
-                // ---- P = exp2(S - m), row sum, split to fp16 hi/lo, back to TMEM over S
-                const float mref = m_run[gi];
-                const uint64_t negm = pack2(-mref, -mref);
-                uint32_t hi[32], lo[32];
+                // ---- P = exp2(S - m), row sum, split to fp16 hi/lo, back to TMEM over S (P_hi: columns 0-31, P_lo: 32-63)
+                const uint64_t negm = pack2(-m_run, -m_run);
                 uint64_t sum2 = pack2(0.f, 0.f);
 #pragma unroll
-                for (int k = 0; k < 32; ++k) {
-                    float x0, x1;
-                    unpack2(add2(s2[k], negm), x0, x1);
-                    const float p0 = ex2(x0), p1 = ex2(x1);
-                    sum2 = add2(sum2, pack2(p0, p1));
-                    split2_pos(p0, p1, hi[k], lo[k]);
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    uint32_t hi[8], lo[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        float x0, x1;
+                        unpack2(add2(s2[q4 * 8 + k], negm), x0, x1);
+                        const float p0 = ex2(x0), p1 = ex2(x1);
+                        sum2 = add2(sum2, pack2(p0, p1));
+                        split2_pos(p0, p1, hi[k], lo[k]);
+                    }
+                    tmem_st8(ts + q4 * 8, hi);
+                    tmem_st8(ts + 32 + q4 * 8, lo);
                 }
                 float sum, sum_b;
                 unpack2(sum2, sum, sum_b);
-                sum += sum_b;
-                l_run[gi] += sum;
-                tmem_st32(tl + COL_S + g * BKV, hi);
-                tmem_st32(tl + COL_S + g * BKV + 32, lo);
+                l_run += sum + sum_b;
                 tmem_st_wait();
                 tc_fence_before();
                 mbar_arrive(smem_u32(&bars.p_ready[g]));
                 if ((warp & 3) == 0) TRACE(j * ng + g, 6);     // P published
             }
-        }
-        // ---- epilogue: O / l -> split planes
-#pragma unroll
-        for (int gi = 0; gi < 2; ++gi) {
-            const int g = wg + 2 * gi;
-            if (g >= ng) continue;
+            // ---- epilogue: O / l -> split planes (O columns 0-31: P_hi V_hi + P_lo V_hi, 32-63: P_hi V_lo)
             mbar_wait(smem_u32(&bars.pv_done[g]), (uint32_t)(NJ - 1) & 1u);
             tc_fence_after();
-            uint32_t o[32], o2[32];
-            tmem_ld32(tl + COL_O + g * 2 * D, o);
-            tmem_ld32(tl + COL_O + g * 2 * D + 32, o2);
-            tmem_ld_wait();
-            const float inv = 1.0f / l_run[gi];
-            uint32_t hi[16], lo[16];
-#pragma unroll
-            for (int k = 0; k < 16; ++k)
-                split2((__uint_as_float(o[2 * k]) + __uint_as_float(o2[2 * k])) * inv,
-                       (__uint_as_float(o[2 * k + 1]) + __uint_as_float(o2[2 * k + 1])) * inv, hi[k], lo[k]);
+            const float inv = 1.0f / l_run;
             const size_t off = ((size_t)(b0 + g) * S + (size_t)qt * BQ + row) * p.c + (size_t)h * D;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                reinterpret_cast<uint4*>(p.oh + off)[k] = make_uint4(hi[4 * k], hi[4 * k + 1], hi[4 * k + 2], hi[4 * k + 3]);
-                reinterpret_cast<uint4*>(p.ol + off)[k] = make_uint4(lo[4 * k], lo[4 * k + 1], lo[4 * k + 2], lo[4 * k + 3]);
+            for (int half = 0; half < 2; ++half) {
+                uint32_t o[16], o2[16];
+                tmem_ld16(to + half * 16, o);
+                tmem_ld16(to + 32 + half * 16, o2);
+                tmem_ld_wait();
+                uint32_t hi[8], lo[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    split2((__uint_as_float(o[2 * k]) + __uint_as_float(o2[2 * k])) * inv,
+                           (__uint_as_float(o[2 * k + 1]) + __uint_as_float(o2[2 * k + 1])) * inv, hi[k], lo[k]);
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    reinterpret_cast<uint4*>(p.oh + off)[half * 2 + k] = make_uint4(hi[4 * k], hi[4 * k + 1], hi[4 * k + 2], hi[4 * k + 3]);
+                    reinterpret_cast<uint4*>(p.ol + off)[half * 2 + k] = make_uint4(lo[4 * k], lo[4 * k + 1], lo[4 * k + 2], lo[4 * k + 3]);
+                }
             }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 9) tmem_dealloc(tmem, TMEM_COLS);
+    if (warp == 4 * G + 1) tmem_dealloc(tmem, TMEM_COLS);
 }
 
 }  // namespace
