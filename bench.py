@@ -143,8 +143,8 @@ def run_reference(args, rank):
 
 def attention_dram_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the attention kernel, from the committed
-    `ncu --set full` capture summarised in profiles/r01_attention_umma_ncu.txt (same shape as the bench)."""
-    p = os.path.join(ROOT, "profiles", "r01_attention_umma_ncu.txt")
+    `ncu --set full` capture summarised in profiles/r01_attn_atom_ncu.txt (same shape as the bench)."""
+    p = os.path.join(ROOT, "profiles", "r01_attn_atom_ncu.txt")
     try:
         tot = 0.0
         for line in open(p):

@@ -44,10 +44,14 @@ struct TBars {
 
 PDK_DEV void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 PDK_DEV void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
-PDK_DEV float silu_mufu(float x) {
+// silu(x0), silu(x1) with ONE MUFU rcp: 1/a = b * rcp(a b), 1/b = a * rcp(a b), a = 1 + exp(-x).  The exponent is clamped
+// to 2^60 so that a*b stays finite; below x = -41.6 silu(x) is then -|x| 2^-60 instead of ~-|x| e^x: both are < 1e-16.
+PDK_DEV void silu2(float x0, float x1, float& s0, float& s1) {
+    const float a = 1.0f + ex2(fminf(-kLog2e * x0, 60.f)), b = 1.0f + ex2(fminf(-kLog2e * x1, 60.f));
     float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + ex2(-kLog2e * x)));
-    return x * r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a * b));
+    s0 = x0 * (b * r);
+    s1 = x1 * (a * r);
 }
 
 __global__ void __launch_bounds__(T_THREADS, 1)
@@ -176,14 +180,15 @@ transition_umma_kernel(const __grid_constant__ CUtensorMap mW13h, const __grid_c
         const uint32_t stg = sm + OFF_H + ew * STG_WARP;
         const int rr = lane >> 1, rc = lane & 1;
         // LayerNorm + modulation of 8 rows per warp -> A planes (SWIZZLE_128B, K-major)
-        auto layer_norm_tile = [&](int t) {
+        auto load_rows = [&](int t, float4 (&v)[8]) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = *reinterpret_cast<const float4*>(p.x + (size_t)(t * TM + ew * 8 + i) * TC + lane * 4);
+        };
+        auto layer_norm_tile = [&](int t, float4 (&v)[8]) {
             const int m0 = t * TM;
             const float* shift = p.mod + (size_t)(m0 / p.rows_per_sample) * p.mod_stride + p.mod_off;
             const float4 sh = *reinterpret_cast<const float4*>(shift + lane * 4);
             const float4 sc = *reinterpret_cast<const float4*>(shift + TC + lane * 4);
-            float4 v[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = *reinterpret_cast<const float4*>(p.x + (size_t)(m0 + ew * 8 + i) * TC + lane * 4);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int row = ew * 8 + i;
@@ -204,14 +209,17 @@ transition_umma_kernel(const __grid_constant__ CUtensorMap mW13h, const __grid_c
         };
         uint32_t g = 0;                               // global hidden-block counter (matches g1 / g2 of the MMA warp)
         int it = 0;
-        if ((int)blockIdx.x < num_tiles) layer_norm_tile(blockIdx.x);
+        float4 vrow[8];                               // the 8 rows this warp normalises (prefetched one block early)
+        if ((int)blockIdx.x < num_tiles) { load_rows(blockIdx.x, vrow); layer_norm_tile(blockIdx.x, vrow); }
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
             const int m0 = t * TM;
             const int row0 = m0 + q * 32;
             const int col = ch * 32;
             // ---- hidden blocks: SiLU(h1) * h3 -> H planes
+            const bool has_next = t + (int)gridDim.x < num_tiles;
             for (int j = 0; j < NT; ++j, ++g) {
                 const uint32_t b = g & 1u;
+                if (j == NT - 1 && has_next) load_rows(t + gridDim.x, vrow);      // latency hidden behind the last hidden block
                 mbar_wait(smem_u32(&bars.acc1_full[b]), (g >> 1) & 1u);
                 tc_fence_after();
                 uint32_t raw[32];
@@ -222,9 +230,11 @@ transition_umma_kernel(const __grid_constant__ CUtensorMap mW13h, const __grid_c
                 if (lane == 0) mbar_arrive(smem_u32(&bars.acc1_empty[b]));
                 uint32_t w[16];     // words 0-7: hi halves of this chunk's 16 hidden values, 8-15: lo halves
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    split2(silu_mufu(__uint_as_float(raw[2 * i])) * __uint_as_float(raw[16 + 2 * i]),
-                           silu_mufu(__uint_as_float(raw[2 * i + 1])) * __uint_as_float(raw[16 + 2 * i + 1]), w[i], w[8 + i]);
+                for (int i = 0; i < 8; ++i) {
+                    float s0, s1;
+                    silu2(__uint_as_float(raw[2 * i]), __uint_as_float(raw[2 * i + 1]), s0, s1);
+                    split2(s0 * __uint_as_float(raw[16 + 2 * i]), s1 * __uint_as_float(raw[16 + 2 * i + 1]), w[i], w[8 + i]);
+                }
                 mbar_wait(smem_u32(&bars.h_empty[b]), ((g >> 1) & 1u) ^ 1u);      // GEMM 2 has consumed the previous content
                 const uint32_t hb = sm + OFF_H + b * 2 * PT + r * 128;
                 const uint32_t c0 = (uint32_t)(((2 * ch) ^ (r & 7)) << 4), c1 = (uint32_t)(((2 * ch + 1) ^ (r & 7)) << 4);
@@ -236,15 +246,18 @@ transition_umma_kernel(const __grid_constant__ CUtensorMap mW13h, const __grid_c
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&bars.h_full[b]));
             }
-            // ---- residual tile of the final epilogue (fetched while GEMM 2 finishes)
-            float4 xres[8];
+            // ---- A operand of the NEXT tile (all GEMM-1 MMAs of this tile have completed: acc1_full of its last block)
+            if (has_next) layer_norm_tile(t + gridDim.x, vrow);
+            // ---- residual tile and gate of the final epilogue, in the write-out layout (fetched while GEMM 2 finishes)
+            float4 xres[8], gate4[4];
+            const float* gate = p.mod + (size_t)(m0 / p.rows_per_sample) * p.mod_stride + p.mod_off + 2 * TC + col;
 #pragma unroll
-            for (int ps = 0; ps < 4; ++ps)
+            for (int ps = 0; ps < 4; ++ps) {
+                gate4[ps] = __ldg(reinterpret_cast<const float4*>(gate + ps * 8 + rc * 4));
 #pragma unroll
                 for (int k = 0; k < 2; ++k)
                     xres[ps * 2 + k] = *reinterpret_cast<const float4*>(p.x + (size_t)(row0 + k * 16 + rr) * TC + col + ps * 8 + rc * 4);
-            // ---- A operand of the NEXT tile (all GEMM-1 MMAs of this tile have completed: acc1_full of its last block)
-            if (t + (int)gridDim.x < num_tiles) layer_norm_tile(t + gridDim.x);
+            }
             // ---- final epilogue: x += acc2 * gate
             mbar_wait(smem_u32(&bars.acc2_full), (uint32_t)it & 1u);
             tc_fence_after();
@@ -254,29 +267,22 @@ transition_umma_kernel(const __grid_constant__ CUtensorMap mW13h, const __grid_c
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&bars.acc2_empty));
-            const float* gate = p.mod + (size_t)(m0 / p.rows_per_sample) * p.mod_stride + p.mod_off + 2 * TC + col;
-            float v[32];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float4 g4 = __ldg(reinterpret_cast<const float4*>(gate) + i);
-                v[4 * i] = __uint_as_float(raw[4 * i]) * g4.x; v[4 * i + 1] = __uint_as_float(raw[4 * i + 1]) * g4.y;
-                v[4 * i + 2] = __uint_as_float(raw[4 * i + 2]) * g4.z; v[4 * i + 3] = __uint_as_float(raw[4 * i + 3]) * g4.w;
-            }
 #pragma unroll
             for (int ps = 0; ps < 4; ++ps) {
                 __syncwarp();
-                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(stg + lane * STG_ROW), "r"(__float_as_uint(v[ps * 8])),
-                             "r"(__float_as_uint(v[ps * 8 + 1])), "r"(__float_as_uint(v[ps * 8 + 2])), "r"(__float_as_uint(v[ps * 8 + 3])) : "memory");
-                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(stg + lane * STG_ROW + 16), "r"(__float_as_uint(v[ps * 8 + 4])),
-                             "r"(__float_as_uint(v[ps * 8 + 5])), "r"(__float_as_uint(v[ps * 8 + 6])), "r"(__float_as_uint(v[ps * 8 + 7])) : "memory");
+                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(stg + lane * STG_ROW), "r"(raw[ps * 8]), "r"(raw[ps * 8 + 1]),
+                             "r"(raw[ps * 8 + 2]), "r"(raw[ps * 8 + 3]) : "memory");
+                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(stg + lane * STG_ROW + 16), "r"(raw[ps * 8 + 4]), "r"(raw[ps * 8 + 5]),
+                             "r"(raw[ps * 8 + 6]), "r"(raw[ps * 8 + 7]) : "memory");
                 __syncwarp();
 #pragma unroll
                 for (int k = 0; k < 2; ++k) {
                     float4 o;
                     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w)
                                  : "r"(stg + (k * 16 + rr) * STG_ROW + rc * 16));
-                    const float4 xr = xres[ps * 2 + k];
-                    o.x += xr.x; o.y += xr.y; o.z += xr.z; o.w += xr.w;
+                    const float4 xr = xres[ps * 2 + k], g4 = gate4[ps];
+                    o.x = __fmaf_rn(o.x, g4.x, xr.x); o.y = __fmaf_rn(o.y, g4.y, xr.y);
+                    o.z = __fmaf_rn(o.z, g4.z, xr.z); o.w = __fmaf_rn(o.w, g4.w, xr.w);
                     *reinterpret_cast<float4*>(p.x + (size_t)(row0 + k * 16 + rr) * TC + col + ps * 8 + rc * 4) = o;
                 }
             }
