@@ -86,9 +86,12 @@ transition_umma_kernel(const __grid_constant__ CUtensorMap mW13h, const __grid_c
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
+#ifndef PDK_TRANS_PARTIAL_WAIT
+    griddep_wait();       // all threads (measured on the GEMM / attention kernels: partial or late waits cost 2-4% of the step)
+#endif
 
     if (warp == 0) {
-        // ================================================================= TMA producer (weights only; no griddep_wait)
+        // ================================================================= TMA producer (weights only)
         int s = 0;
         uint32_t ph = 0;
         auto load = [&](const CUtensorMap* mh, const CUtensorMap* ml, int c0, int c1) {
@@ -172,7 +175,9 @@ transition_umma_kernel(const __grid_constant__ CUtensorMap mW13h, const __grid_c
         }
     } else {
         // ================================================================= LN / epilogue warps
+#ifdef PDK_TRANS_PARTIAL_WAIT
         griddep_wait();                               // x and mod come from the preceding kernels
+#endif
         const int ew = warp - 2;
         const int q = warp & 3;                       // TMEM lane quarter
         const int ch = ew >> 2;                       // 32-column chunk of a 128-column accumulator

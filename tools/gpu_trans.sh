@@ -2,7 +2,7 @@
 mkdir -p gpurun_out
 {
 echo "== fused transition test"
-timeout 300 python -m pytest tests/test_gpu_ops.py -m gpu -q --tb=short -p no:cacheprovider -x -k "fused_atom_transition" 2>&1 | tail -25
+timeout 300 python -m pytest tests/test_gpu_ops.py -m gpu -q --tb=short -p no:cacheprovider -x -k "gemm or attention or transition or qkv" 2>&1 | tail -25
 timeout 200 python tools/time_gemm.py 2>&1 | grep "fused\|adaln"
 echo "== all gpu tests"
 timeout 900 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider -x 2>&1 | tail -5
