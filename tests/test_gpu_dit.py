@@ -71,6 +71,22 @@ def test_denoiser_256_2048_vs_oracle(dit):
     assert r < TOL_A, r
 
 
+def test_denoiser_384_3072_vs_oracle(dit):
+    """BASELINE.json configs[2] shape (crop 384 / atom crop 3072) against the CPU oracle, ragged token layout, B=2."""
+    dims, sd, _ = medium_state()
+    cx = make_complex(384, 3072, dims, seed=4, ragged=True)
+    g = torch.Generator().manual_seed(6)
+    x_hat = torch.randn(2, 3072, 3, generator=g) * 30
+    t_hat = torch.tensor([25.0, 1.5])
+    with torch.no_grad():
+        want = O.af3dit_forward(sd, cx, x_hat, t_hat, cx["a"], cx["ap"], cx["s"], cx["z"])
+    d = to_dev(cx)
+    got = dit(d, x_hat.to(DEV), t_hat.to(DEV), d["a"], d["ap"], d["s"], d["z"]).cpu()
+    r = float(O.rmsd(got, want).max())
+    log_value("dit384/3072 rmsd", r)
+    assert r < TOL_A, r
+
+
 def test_dropin_contract_and_caching(dit):
     """forward() has AF3DiT's signature; the per-complex cache is keyed on the conditioning tensors."""
     cx = to_dev(complex_64_512())

@@ -67,6 +67,26 @@ def test_attention_vs_fp64(B, H, S):
     rel_close("attention", got, want, rtol=0, atol=3e-6 * float(want.abs().max()))
 
 
+def test_attention_many_samples_chunked_work_list():
+    """BASELINE.json configs[2]-sized call (Na = 3072, dozens of samples): the work list no longer fits the kernel
+    parameters and launch_attention splits the samples into several launches (attention_umma.cu: kMaxWork)."""
+    from physdock_b200 import ops
+    B, H, S = 40, 4, 3072
+    g = torch.Generator(device=DEV).manual_seed(77)
+    q, k, v = [torch.randn(B, H, S, 32, generator=g, device=DEV) * s for s in (2.0, 2.0, 1.0)]
+    bias = torch.randn(H, S, S, generator=g, device=DEV) * 2
+    bias[:, :, S - 7:] = -1e9
+    scale = ops.LOG2E / math.sqrt(32.0)
+    planes = [ops.interleave_planes(q * scale), ops.interleave_planes(k), ops.interleave_planes(v)]
+    oh, ol = ops.attention(*planes, (bias * ops.LOG2E).contiguous())
+    got = ops.planes_to_float(oh, ol).view(B, S, H, 32).transpose(1, 2)
+    for b in (0, 19, 20, 39):         # B = 40 is launched as 20 + 20: samples on both sides of the boundary, fp64 reference per sample
+        want = torch.softmax(q[b].double() @ k[b].double().transpose(-1, -2) / math.sqrt(32.0) + bias.double(), -1) @ v[b].double()
+        # 3072 keys = 192 sequential fp32 accumulations in TMEM per output (tensor-core accumulation truncates): the
+        # error grows with the key count, 5.6e-6 of the scale here against 3e-6 allowed at S <= 640
+        rel_close(f"attention sample {b}", got[b], want, rtol=0, atol=1e-5 * float(want.abs().max()))
+
+
 # ------------------------------------------------------------------------------------- conditioning
 def test_time_embed_and_coef(env):
     from physdock_b200 import ops
