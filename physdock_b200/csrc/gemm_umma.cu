@@ -202,14 +202,24 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant_
                          : "r"(stg + (it * 16 + rr) * STG_ROW_BYTES + rc * 16));
             return v;
         };
+        // Tile coordinates are advanced incrementally and the sample index uses a multiply-high reciprocal: the integer
+        // divisions of the first version (t / num_n, m0 / rows_per_sample, col / c, ...) were ~200 of the ~600
+        // instructions each epilogue thread executed per tile (IABS / I2F.RP chains in profiles/r01_gemm_qkv_ncu.txt).
+        int tm = worker / num_n, tn = worker % num_n;
+        const int dm = nworkers / num_n, dn = nworkers % num_n;
+        const uint32_t tiles_per_sample = (uint32_t)(p.rows_per_sample > 0 ? p.rows_per_sample / BM : 1);
+        const uint32_t tps_magic = (uint32_t)((0x100000000ull + tiles_per_sample - 1) / tiles_per_sample);   // exact for mt, d < 2^16; d == 1 handled separately (2^32 does not fit)
         int lt = 0;
         for (int t = worker; t < num_tiles; t += nworkers, ++lt) {
             const int buf = lt & 1;
-            const int m0 = (t / num_n) * TILE_M + (int)rank * BM, n0 = (t % num_n) * BN;
+            const int mt = (PAIR ? 2 * tm : tm) + (int)rank;      // index of this CTA's 128-row tile
+            const int m0 = mt * BM, n0 = tn * BN;
+            tm += dm; tn += dn;
+            if (tn >= num_n) { tn -= num_n; ++tm; }
             const int row0 = m0 + q * 32;             // first row of this warp; this thread computes row0 + lane
             const int col = n0 + ch * 32;
             // a 128-row tile never straddles samples (rows_per_sample % 128 == 0)
-            const int sample = (EPI == EPI_GATE_RESID || EPI == EPI_QKV) ? m0 / p.rows_per_sample : 0;
+            const int sample = (EPI == EPI_GATE_RESID || EPI == EPI_QKV) ? (tiles_per_sample == 1 ? mt : (int)__umulhi((uint32_t)mt, tps_magic)) : 0;
             float4 xres[8];                           // EPI_GATE_RESID: the residual values this lane will update
             if constexpr (EPI == EPI_GATE_RESID) {
 #pragma unroll
@@ -295,8 +305,8 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant_
 #endif
                 }
             } else {   // EPI_QKV: this chunk is one head of q, k or v
-                const int which = col / p.c;
-                const int head = (col % p.c) / kHeadDim;
+                const int which = col >> p.c_shift;                          // c is a power of two (128 or 512)
+                const int head = (col & (p.c - 1)) / kHeadDim;
                 const int H = p.c / kHeadDim;
                 if (which < 2) {    // per-head RMSNorm (rms_norm.py:14-19); q additionally carries log2e/sqrt(32)
                     float ss = 0.f;
@@ -311,7 +321,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant_
                     }
                 }
                 __half* dbase = which == 0 ? p.q : (which == 1 ? p.k : p.v);      // row = [hi 32 | lo 32] halves = 128 bytes
-                const size_t tile_row = (size_t)(sample * H + head) * p.rows_per_sample + (row0 % p.rows_per_sample);
+                const size_t tile_row = (size_t)(sample * H + head) * p.rows_per_sample + (row0 - sample * p.rows_per_sample);
                 uint32_t hi[16], lo[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) split2(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
@@ -394,9 +404,13 @@ cudaError_t launch_gemm(GemmEpilogue epi, const GemmArgs& a, cudaStream_t st) {
         case EPI_STORE: return launch_one<EPI_STORE>(a, st);
         case EPI_GATE_RESID: return launch_one<EPI_GATE_RESID>(a, st);
         case EPI_SWIGLU: return launch_one<EPI_SWIGLU>(a, st);
-        case EPI_QKV:
-            if (a.N != 3 * a.c || a.c % BN) return cudaErrorInvalidValue;
-            return launch_one<EPI_QKV>(a, st);
+        case EPI_QKV: {
+            if (a.N != 3 * a.c || a.c % BN || (a.c & (a.c - 1))) return cudaErrorInvalidValue;      // c: power of two >= 128
+            GemmArgs b = a;
+            b.c_shift = 0;
+            while ((1 << b.c_shift) < a.c) ++b.c_shift;
+            return launch_one<EPI_QKV>(b, st);
+        }
     }
     return cudaErrorInvalidValue;
 }

@@ -29,7 +29,8 @@ struct GemmArgs {
     __half* ph; __half* pl; int ldp;   // EPI_SWIGLU output planes [M, N/2]
     __half* q; __half* k; __half* v;   // EPI_QKV: [B,H,S_pad,64] rows = [hi 32 | lo 32] (128-byte rows for TMA)
     const float* norm_q; const float* norm_k;   // [32] RMSNorm gains
-    int c;                      // model width (N == 3c)
+    int c;                      // model width (N == 3c), a power of two
+    int c_shift;                // log2(c), filled in by launch_gemm
     float rms_eps; float q_scale;
 };
 cudaError_t launch_gemm(GemmEpilogue epi, const GemmArgs& a, cudaStream_t st);
