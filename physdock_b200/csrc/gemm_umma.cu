@@ -37,14 +37,23 @@ namespace {
 // tests/cuda/umma_probe.cu test 7), which made the BK = 32 version L2-fabric bound.
 constexpr int BM = 128, BN = 128, BK = 64, ACC = 2;
 constexpr int TILE_BYTES = 128 * BK * 2;            // 16 KB: one fp16 plane tile of 128 rows, 128-byte rows (SWIZZLE_128B)
-constexpr int RING_BYTES = 192 * 1024;
+constexpr int RING_BYTES = 192 * 1024;            // NARROW staging: 3 stages (single CTA) / 4 stages (pair)
 // Epilogue staging: a thread owns one output ROW, so storing straight from registers makes every store instruction
 // scatter 16 bytes to 32 different rows (measured: 14 of 36 us on the atom SwiGLU GEMM).  Each epilogue warp therefore
 // parks 8 words per row in a private padded smem tile (48-byte rows: conflict-free 128-bit writes and reads) and
 // writes it out row-contiguously, 16 rows x 32 bytes per instruction.
 constexpr int EPI_WARPS = 16;
 constexpr int STG_ROW_BYTES = 48, STG_WARP_BYTES = 32 * STG_ROW_BYTES;
-constexpr int SMEM_BYTES = RING_BYTES + EPI_WARPS * STG_WARP_BYTES + 1024;   // + slack to 1024-align the ring
+// WIDE staging (template flag): the warp parks all 32 words of its rows (144-byte rows, conflict-free) and writes them
+// out as 4 rows x 128 contiguous bytes per instruction.  The 8-word / 32-byte version costs 16 L1 wavefronts per store
+// instruction (16 different lines), and the store-heavy epilogues (QKV: 64 KB per tile) were LSU-bound
+// (profiles/r01_gemm_qkv_ncu.txt: l1tex 50%, 9 k cycles per tile against 1.5-6 k of MMA).  It needs 72 KB of staging, so
+// the ring drops one stage: used where the ring is deep enough anyway (pair tiling) or K = 128 (two stages = a whole tile).
+constexpr int WSTG_ROW_BYTES = 144, WSTG_WARP_BYTES = 32 * WSTG_ROW_BYTES;
+template <bool PAIR, bool WIDE> __host__ __device__ constexpr int ring_stages() { return PAIR ? (WIDE ? 3 : 4) : (WIDE ? 2 : 3); }
+template <bool PAIR, bool WIDE> __host__ __device__ constexpr int smem_bytes() {
+    return ring_stages<PAIR, WIDE>() * (PAIR ? 48 : 64) * 1024 + EPI_WARPS * (WIDE ? WSTG_WARP_BYTES : STG_WARP_BYTES) + 1024;
+}
 constexpr int NTHREADS = (2 + EPI_WARPS) * 32;
 constexpr uint32_t TMEM_COLS = ACC * BN;
 
@@ -59,14 +68,15 @@ PDK_DEV float silu_fast(float x) {
     return x * r;
 }
 
-template <int EPI, bool PAIR>
+template <int EPI, bool PAIR, bool WIDE>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_umma_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUtensorMap mAl,
                  const __grid_constant__ CUtensorMap mWh, const __grid_constant__ CUtensorMap mWl, const GemmArgs p) {
     constexpr int W_ROWS = PAIR ? BN / 2 : BN;                  // W rows this CTA loads per stage
     constexpr int W_TILE = W_ROWS * BK * 2;
     constexpr int STAGE_BYTES = 2 * TILE_BYTES + 2 * W_TILE;    // A_hi, A_lo, W_hi, W_lo: 48 KB (pair) / 64 KB
-    constexpr int STAGES = RING_BYTES / STAGE_BYTES;            // 4 / 3
+    constexpr int STAGES = ring_stages<PAIR, WIDE>();
+    static_assert(STAGES * STAGE_BYTES <= RING_BYTES, "ring");
     constexpr int TILE_M = PAIR ? 2 * BM : BM;
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[2 * STAGES + 2 * ACC];
@@ -187,8 +197,24 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant_
         const int ew = warp - 2;
         const int q = warp & 3;                       // TMEM lane quarter this warp may access
         const int ch = ew >> 2;                       // warps 2-5: chunk 0, 6-9: 1, 10-13: 2, 14-17: 3 (each group covers all quarters)
-        const uint32_t stg = ring + STAGES * STAGE_BYTES + ew * STG_WARP_BYTES;
+        const uint32_t stg = ring + STAGES * STAGE_BYTES + ew * (WIDE ? WSTG_WARP_BYTES : STG_WARP_BYTES);
         const int rr = lane >> 1, rc = lane & 1;      // write-out role: row (within a group of 16) and 16-byte piece
+        const int wr = lane >> 3, wc = lane & 7;      // WIDE write-out role: row (within a group of 4) and 16-byte piece of 128
+        // WIDE: park all 32 words of this thread's row; lane then copies piece wc of rows it*4 + wr, it = 0..7
+        auto stage32 = [&](const uint32_t (&w)[32]) {
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(stg + lane * WSTG_ROW_BYTES + i * 16), "r"(w[4 * i]),
+                             "r"(w[4 * i + 1]), "r"(w[4 * i + 2]), "r"(w[4 * i + 3]) : "memory");
+            __syncwarp();
+        };
+        auto unstage_w = [&](int it) {
+            uint4 v;
+            asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                         : "r"(stg + (it * 4 + wr) * WSTG_ROW_BYTES + wc * 16));
+            return v;
+        };
         // park 8 words of this thread's row, then hand each lane 4 consecutive words of rows rr and 16 + rr
         auto stage8 = [&](uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4, uint32_t w5, uint32_t w6, uint32_t w7) {
             __syncwarp();
@@ -222,11 +248,17 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant_
             const int sample = (EPI == EPI_GATE_RESID || EPI == EPI_QKV) ? (tiles_per_sample == 1 ? mt : (int)__umulhi((uint32_t)mt, tps_magic)) : 0;
             float4 xres[8];                           // EPI_GATE_RESID: the residual values this lane will update
             if constexpr (EPI == EPI_GATE_RESID) {
+                if constexpr (WIDE) {
 #pragma unroll
-                for (int ps = 0; ps < 4; ++ps)
+                    for (int it = 0; it < 8; ++it)
+                        xres[it] = *reinterpret_cast<const float4*>(p.out + (size_t)(row0 + it * 4 + wr) * p.ldo + col + wc * 4);
+                } else {
 #pragma unroll
-                    for (int it = 0; it < 2; ++it)
-                        xres[ps * 2 + it] = *reinterpret_cast<const float4*>(p.out + (size_t)(row0 + it * 16 + rr) * p.ldo + col + ps * 8 + rc * 4);
+                    for (int ps = 0; ps < 4; ++ps)
+#pragma unroll
+                        for (int it = 0; it < 2; ++it)
+                            xres[ps * 2 + it] = *reinterpret_cast<const float4*>(p.out + (size_t)(row0 + it * 16 + rr) * p.ldo + col + ps * 8 + rc * 4);
+                }
             }
             mbar_wait(tfull(buf), ((uint32_t)lt >> 1) & 1u);
             tc_fence_after();
@@ -269,6 +301,23 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant_
                         v[4 * i] *= g4.x; v[4 * i + 1] *= g4.y; v[4 * i + 2] *= g4.z; v[4 * i + 3] *= g4.w;
                     }
                 }
+                if constexpr (WIDE) {
+                    uint32_t w[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) w[i] = __float_as_uint(v[i]);
+                    stage32(w);
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const uint4 u = unstage_w(it);
+                        float4* dst = reinterpret_cast<float4*>(p.out + (size_t)(row0 + it * 4 + wr) * p.ldo + col + wc * 4);
+                        float4 o = make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w));
+                        if constexpr (EPI == EPI_GATE_RESID) {
+                            const float4 x = xres[it];
+                            o.x += x.x; o.y += x.y; o.z += x.z; o.w += x.w;
+                        }
+                        *dst = o;
+                    }
+                } else
 #pragma unroll
                 for (int ps = 0; ps < 4; ++ps) {
                     stage8(__float_as_uint(v[ps * 8]), __float_as_uint(v[ps * 8 + 1]), __float_as_uint(v[ps * 8 + 2]), __float_as_uint(v[ps * 8 + 3]),
@@ -322,6 +371,18 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant_
                 }
                 __half* dbase = which == 0 ? p.q : (which == 1 ? p.k : p.v);      // row = [hi 32 | lo 32] halves = 128 bytes
                 const size_t tile_row = (size_t)(sample * H + head) * p.rows_per_sample + (row0 - sample * p.rows_per_sample);
+                if constexpr (WIDE) {
+                    uint32_t w[32];                   // the 128-byte output row: 16 words hi | 16 words lo
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) split2(v[2 * i], v[2 * i + 1], w[i], w[16 + i]);
+                    stage32(w);
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const uint4 u = unstage_w(it);
+                        *reinterpret_cast<uint4*>(dbase + (tile_row + it * 4 + wr) * (2 * kHeadDim) + wc * 8) = u;
+                    }
+                    continue;
+                }
                 uint32_t hi[16], lo[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) split2(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
@@ -347,11 +408,13 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant_
     }
 }
 
-template <int EPI, bool PAIR>
+template <int EPI, bool PAIR, bool WIDE>
 cudaError_t launch_variant(const GemmArgs& a, cudaStream_t st, int num_sms) {
+    constexpr int SMEM_BYTES = smem_bytes<PAIR, WIDE>();
+    static_assert(SMEM_BYTES <= 227 * 1024, "shared memory");
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_umma_kernel<EPI, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(gemm_umma_kernel<EPI, PAIR, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (e != cudaSuccess) return e;
         configured = true;
     }
@@ -373,7 +436,7 @@ cudaError_t launch_variant(const GemmArgs& a, cudaStream_t st, int num_sms) {
     attr[1].id = cudaLaunchAttributeClusterDimension;
     attr[1].val.clusterDim.x = 2; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = PAIR ? 2 : 1;
-    PDK_LAUNCH_CHECK(cudaLaunchKernelEx(&cfg, gemm_umma_kernel<EPI, PAIR>, mAh, mAl, mWh, mWl, a));
+    PDK_LAUNCH_CHECK(cudaLaunchKernelEx(&cfg, gemm_umma_kernel<EPI, PAIR, WIDE>, mAh, mAl, mWh, mWl, a));
     return cudaGetLastError();
 }
 
@@ -389,8 +452,16 @@ cudaError_t launch_one(const GemmArgs& a, cudaStream_t st) {
     static const bool allow_pair = getenv("PDK_NO_PAIR") == nullptr;       // measurement switch
     static const bool force_pair = getenv("PDK_FORCE_PAIR") != nullptr;    // measurement switch
     const bool big = (long long)a.K * a.N >= 700000;       // see the header: small-K shapes lose on the pair tiling
-    if (allow_pair && a.M % (2 * BM) == 0 && (big || force_pair)) return launch_variant<EPI, true>(a, st, num_sms);
-    return launch_variant<EPI, false>(a, st, num_sms);
+    static const bool allow_wide = getenv("PDK_NO_WIDE") == nullptr;       // measurement switch
+    const bool pair = allow_pair && a.M % (2 * BM) == 0 && (big || force_pair);
+    if constexpr (EPI == EPI_SWIGLU) {        // 32-byte rows per plane either way: always the narrow staging
+        return pair ? launch_variant<EPI, true, false>(a, st, num_sms) : launch_variant<EPI, false, false>(a, st, num_sms);
+    } else {
+        static const bool wide_all = getenv("PDK_WIDE_ALL") != nullptr;      // measurement switch
+        const bool wide = allow_wide && (pair || a.K <= 2 * BK || wide_all);
+        if (pair) return wide ? launch_variant<EPI, true, true>(a, st, num_sms) : launch_variant<EPI, true, false>(a, st, num_sms);
+        return wide ? launch_variant<EPI, false, true>(a, st, num_sms) : launch_variant<EPI, false, false>(a, st, num_sms);
+    }
 }
 
 }  // namespace
