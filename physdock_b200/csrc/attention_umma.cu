@@ -364,22 +364,40 @@ attention_umma_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_const
             mbar_wait(smem_u32(&bars.pv_done[g]), (uint32_t)(NJ - 1) & 1u);
             tc_fence_after();
             const float inv = 1.0f / l_run;
-            const size_t off = ((size_t)(b0 + g) * S + (size_t)qt * BQ + row) * p.c + (size_t)h * D;
+            // Row-contiguous write-out: a thread owns one row, so storing from registers makes every store instruction touch
+            // 32 different 128-byte lines (32 L1 wavefronts).  The rows are parked in this sample's Q tile (dead: its last
+            // QK MMA has completed) with 80-byte rows and written as 8 rows x 64 bytes per instruction.
+            const uint32_t stg = sm + OFF_Q + g * Q_TILE + (warp & 3) * (32 * 80);
+            const int wr = lane >> 2, wc = lane & 3;
+            uint32_t hi[16], lo[16];
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 uint32_t o[16], o2[16];
                 tmem_ld16(to + half * 16, o);
                 tmem_ld16(to + 32 + half * 16, o2);
                 tmem_ld_wait();
-                uint32_t hi[8], lo[8];
 #pragma unroll
                 for (int k = 0; k < 8; ++k)
                     split2((__uint_as_float(o[2 * k]) + __uint_as_float(o2[2 * k])) * inv,
-                           (__uint_as_float(o[2 * k + 1]) + __uint_as_float(o2[2 * k + 1])) * inv, hi[k], lo[k]);
+                           (__uint_as_float(o[2 * k + 1]) + __uint_as_float(o2[2 * k + 1])) * inv, hi[half * 8 + k], lo[half * 8 + k]);
+            }
 #pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    reinterpret_cast<uint4*>(p.oh + off)[half * 2 + k] = make_uint4(hi[4 * k], hi[4 * k + 1], hi[4 * k + 2], hi[4 * k + 3]);
-                    reinterpret_cast<uint4*>(p.ol + off)[half * 2 + k] = make_uint4(lo[4 * k], lo[4 * k + 1], lo[4 * k + 2], lo[4 * k + 3]);
+            for (int plane = 0; plane < 2; ++plane) {       // 0: hi, 1: lo
+                const uint32_t* w = plane == 0 ? hi : lo;
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(stg + lane * 80 + i * 16), "r"(w[4 * i]), "r"(w[4 * i + 1]),
+                                 "r"(w[4 * i + 2]), "r"(w[4 * i + 3]) : "memory");
+                __syncwarp();
+                __half* dst = plane == 0 ? p.oh : p.ol;
+#pragma unroll
+                for (int it = 0; it < 4; ++it) {
+                    uint4 u;
+                    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w)
+                                 : "r"(stg + (it * 8 + wr) * 80 + wc * 16));
+                    const size_t off = ((size_t)(b0 + g) * S + (size_t)qt * BQ + (warp & 3) * 32 + it * 8 + wr) * p.c + (size_t)h * D + wc * 8;
+                    *reinterpret_cast<uint4*>(dst + off) = u;
                 }
             }
         }
