@@ -1,3 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_ops.py tests/test_gpu_dit.py -m gpu -q --tb=short -p no:cacheprovider -x -k "chunked or 384" 2>&1 | tail -15 | tee gpurun_out/t.log
+{
+timeout 900 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider -x 2>&1 | tail -6
+for i in 1 2; do timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | grep -o '"ms_per_step[^,]*' | head -1; done
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:time_embed -c 3 python bench.py --steps 2 --warmup 3 --no-cpu-baseline 2>&1 | grep -A3 "time_embed" | grep "gpu__time" | tail -2
+} 2>&1 | tee gpurun_out/t.log
