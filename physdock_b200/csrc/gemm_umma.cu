@@ -381,8 +381,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant_
                         const uint4 u = unstage_w(it);
                         *reinterpret_cast<uint4*>(dbase + (tile_row + it * 4 + wr) * (2 * kHeadDim) + wc * 8) = u;
                     }
-                    continue;
-                }
+                } else {
                 uint32_t hi[16], lo[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) split2(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
@@ -395,6 +394,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant_
                         const uint4 u = unstage(it);
                         *reinterpret_cast<uint4*>(dbase + (tile_row + it * 16 + rr) * (2 * kHeadDim) + ps * 16 + rc * 8) = u;
                     }
+                }
                 }
             }
         }
