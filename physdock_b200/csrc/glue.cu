@@ -50,30 +50,22 @@ __global__ void __launch_bounds__(256) time_embed_kernel(const float* __restrict
         proj[128 + tid] = sn;
     }
     __syncthreads();
-    // warp = 32 output features, one after the other; the lanes split a weight row into two coalesced 512-byte reads and
-    // a shuffle tree adds the partial dot products.  (Thread-per-output made every load instruction touch 32 different
-    // rows = 32 L1 wavefronts: 25 us for this 2 x 256 x 256 MLP.)
-    const int warp = tid >> 5, lane = tid & 31;
-    auto matvec = [&](const float* __restrict__ w, const float* __restrict__ bias, const float* x, float* y) {
-        const float4 x0 = reinterpret_cast<const float4*>(x)[lane], x1 = reinterpret_cast<const float4*>(x)[32 + lane];
+    // thread = one output feature.  The weights arrive TRANSPOSED ([in][out]): a warp's 32 outputs read 128 contiguous
+    // bytes per input feature (1 L1 wavefront per load instead of the 32 of a row-major walk), 256 independent loads.
+    auto matvec = [&](const float* __restrict__ wT, const float* x) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll 8
-        for (int i = 0; i < 32; ++i) {
-            const int o = warp * 32 + i;
-            const float4* row = reinterpret_cast<const float4*>(w + (size_t)o * kTimeDim);
-            const float4 w0 = __ldg(row + lane), w1 = __ldg(row + 32 + lane);
-            // same summation tree for every output: 4 partial sums per lane, then across lanes
-            float a0 = fmaf(w1.x, x1.x, w0.x * x0.x), a1 = fmaf(w1.y, x1.y, w0.y * x0.y);
-            float a2 = fmaf(w1.z, x1.z, w0.z * x0.z), a3 = fmaf(w1.w, x1.w, w0.w * x0.w);
-            const float sdot = warp_sum((a0 + a1) + (a2 + a3));
-            if (lane == 0) y[o] = silu(sdot + bias[o]);
+        for (int k = 0; k < kTimeDim; k += 4) {
+            a0 = fmaf(__ldg(wT + (size_t)(k + 0) * kTimeDim + tid), x[k + 0], a0);
+            a1 = fmaf(__ldg(wT + (size_t)(k + 1) * kTimeDim + tid), x[k + 1], a1);
+            a2 = fmaf(__ldg(wT + (size_t)(k + 2) * kTimeDim + tid), x[k + 2], a2);
+            a3 = fmaf(__ldg(wT + (size_t)(k + 3) * kTimeDim + tid), x[k + 3], a3);
         }
+        return (a0 + a1) + (a2 + a3);
     };
-    __shared__ __align__(16) float outv[kTimeDim];
-    matvec(w1, b1, proj, hid);                        // linear_1 + SiLU
+    hid[tid] = silu(matvec(w1, proj) + b1[tid]);      // linear_1 + SiLU
     __syncthreads();
-    matvec(w2, b2, hid, outv);                        // linear_2, then the SiLU every AdaLN applies first
-    __syncthreads();
-    const float out = outv[tid];
+    const float out = silu(matvec(w2, hid) + b2[tid]);   // linear_2, then the SiLU every AdaLN applies first
     if (tsilu != nullptr) tsilu[(size_t)b * kTimeDim + tid] = out;
     if (ts_h != nullptr) {
         const __half h = __float2half_rn(out);
@@ -190,11 +182,11 @@ __global__ void __launch_bounds__(256) precond_kernel(const float* __restrict__ 
     griddep_launch();
     griddep_wait();
     const int per_row = c_a / 4;
-    const size_t total = (size_t)B * S_pad * per_row;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int c4 = (int)(i % per_row);
-        const size_t r = i / per_row;
-        const int s = (int)(r % S_pad), b = (int)(r / S_pad);
+    const uint32_t total = (uint32_t)B * S_pad * per_row;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {      // 32-bit: launch checks total < 2^31
+        const int c4 = (int)(i % (uint32_t)per_row);
+        const uint32_t r = i / (uint32_t)per_row;
+        const int s = (int)(r % (uint32_t)S_pad), b = (int)(r / (uint32_t)S_pad);
         float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
         if (s < Na) {
             const float c_in = coef[4 * b];
@@ -221,11 +213,11 @@ __global__ void __launch_bounds__(256) segment_mean_kernel(const float* __restri
     griddep_launch();
     griddep_wait();
     const int per_row = c_s / 4;
-    const size_t total = (size_t)B * St_pad * per_row;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int c4 = (int)(i % per_row);
-        const size_t r = i / per_row;
-        const int tok = (int)(r % St_pad), b = (int)(r / St_pad);
+    const uint32_t total = (uint32_t)B * St_pad * per_row;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {      // 32-bit: launch checks total < 2^31
+        const int c4 = (int)(i % (uint32_t)per_row);
+        const uint32_t r = i / (uint32_t)per_row;
+        const int tok = (int)(r % (uint32_t)St_pad), b = (int)(r / (uint32_t)St_pad);
         float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
         if (tok < Nt) {
             const int a0 = tok_start[tok], a1 = tok_start[tok + 1];
@@ -251,11 +243,11 @@ __global__ void __launch_bounds__(256) gather_add_kernel(float* __restrict__ ba,
     griddep_launch();
     griddep_wait();
     const int per_row = c_a / 4;
-    const size_t total = (size_t)B * Na * per_row;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int c4 = (int)(i % per_row);
-        const size_t r = i / per_row;
-        const int at = (int)(r % Na), b = (int)(r / Na);
+    const uint32_t total = (uint32_t)B * Na * per_row;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {      // 32-bit: launch checks total < 2^31
+        const int c4 = (int)(i % (uint32_t)per_row);
+        const uint32_t r = i / (uint32_t)per_row;
+        const int at = (int)(r % (uint32_t)Na), b = (int)(r / (uint32_t)Na);
         const int tok = atom2tok[at];
         float4* dst = reinterpret_cast<float4*>(ba + ((size_t)b * Sa_pad + at) * c_a) + c4;
         const float4 u = *(reinterpret_cast<const float4*>(up + ((size_t)b * St_pad + tok) * c_a) + c4);
@@ -344,14 +336,14 @@ cudaError_t launch_split(const float* x, __half* xh, __half* xl, size_t n, cudaS
 
 cudaError_t launch_precond(const float* x_hat, const float* coef, const float* a, const float* wx, const float* bx,
                            float* ba, int B, int Na, int S_pad, int c_a, cudaStream_t st) {
-    if (c_a % 4 || Na > S_pad) return cudaErrorInvalidValue;
+    if (c_a % 4 || Na > S_pad || (size_t)B * S_pad * (c_a / 4) >= (1ull << 31)) return cudaErrorInvalidValue;
     PDK_LAUNCH_CHECK(launch_pdl(precond_kernel, dim3(grid_for((size_t)B * S_pad * (c_a / 4))), dim3(256), (size_t)(0), st, x_hat, coef, a, wx, bx, ba, B, Na, S_pad, c_a));
     return cudaGetLastError();
 }
 
 cudaError_t launch_segment_mean(const float* h, const int* tok_start, const float* s, float* bs, int B, int Nt,
                                 int Sa_pad, int St_pad, int c_s, cudaStream_t st) {
-    if (c_s % 4 || Nt > St_pad) return cudaErrorInvalidValue;
+    if (c_s % 4 || Nt > St_pad || (size_t)B * St_pad * (c_s / 4) >= (1ull << 31)) return cudaErrorInvalidValue;
     PDK_LAUNCH_CHECK(launch_pdl(segment_mean_kernel, dim3(grid_for((size_t)B * St_pad * (c_s / 4))), dim3(256), (size_t)(0), st, h, tok_start, s, bs, B, Nt, Sa_pad,
                                                                                St_pad, c_s));
     return cudaGetLastError();
@@ -359,7 +351,7 @@ cudaError_t launch_segment_mean(const float* h, const int* tok_start, const floa
 
 cudaError_t launch_gather_add(float* ba, const float* up, const int* atom2tok, int B, int Na, int Sa_pad,
                               int St_pad, int c_a, cudaStream_t st) {
-    if (c_a % 4) return cudaErrorInvalidValue;
+    if (c_a % 4 || (size_t)B * Na * (c_a / 4) >= (1ull << 31)) return cudaErrorInvalidValue;
     PDK_LAUNCH_CHECK(launch_pdl(gather_add_kernel, dim3(grid_for((size_t)B * Na * (c_a / 4))), dim3(256), (size_t)(0), st, ba, up, atom2tok, B, Na, Sa_pad, St_pad, c_a));
     return cudaGetLastError();
 }
