@@ -56,7 +56,7 @@ typedef struct {          /* one DiTBlock (transformers.py:149-159); all device 
 
 typedef struct {
     const float* freq;                        /* [128] exp(-ln(1e4) k/128)  (timestep_embeddings.py:62-67) */
-    const float* te_w1; const float* te_b1; const float* te_w2; const float* te_b2;   /* weights TRANSPOSED [in 256][out 256], biases [256] */
+    const float* te_w1; const float* te_b1; const float* te_w2; const float* te_b2;   /* [256,256],[256] x2 */
     const void* wmod_h; const void* wmod_l;   /* fp16 planes [n_mod,256]: every AdaLayerNormZero.linear, concatenated */
     const float* bmod;                        /* [n_mod] */
     const float* wx; const float* bx;         /* linear_x [c_a,3],[c_a] */
@@ -149,7 +149,6 @@ int pdk_descent_update(const float* x, const float* grad, const uint8_t* in_rows
  * ---------------------------------------------------------------------------------------------- */
 int pdk_op_pair_bias(const float* pair, const float* mask, const float* wfoldT, const float* bfold, float* bias,
                      int64_t S, int64_t S_pad, int64_t C, int64_t LH, float ln_eps, float inf_, void* stream);
-/* w1, w2: the two TimestepEmbedding weights TRANSPOSED ([in 256][out 256]) */
 int pdk_op_time_embed(const float* t_hat, const float* freq, const float* w1, const float* b1, const float* w2,
                       const float* b2, float sigma_data, float* tsilu, float* coef, int64_t B, void* stream);
 int pdk_op_mod_gemv(const float* tsilu, const float* wmod, const float* bmod, float* mod, int64_t B,

@@ -50,16 +50,15 @@ __global__ void __launch_bounds__(256) time_embed_kernel(const float* __restrict
         proj[128 + tid] = sn;
     }
     __syncthreads();
-    // thread = one output feature.  The weights arrive TRANSPOSED ([in][out]): a warp's 32 outputs read 128 contiguous
-    // bytes per input feature (1 L1 wavefront per load instead of the 32 of a row-major walk), 256 independent loads.
-    auto matvec = [&](const float* __restrict__ wT, const float* x) {
+    // thread = one output feature; 64 independent float4 loads per layer keep the (L2-resident) weight rows streaming
+    auto matvec = [&](const float* __restrict__ w, const float* x) {
+        const float4* row = reinterpret_cast<const float4*>(w + (size_t)tid * kTimeDim);
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 8
-        for (int k = 0; k < kTimeDim; k += 4) {
-            a0 = fmaf(__ldg(wT + (size_t)(k + 0) * kTimeDim + tid), x[k + 0], a0);
-            a1 = fmaf(__ldg(wT + (size_t)(k + 1) * kTimeDim + tid), x[k + 1], a1);
-            a2 = fmaf(__ldg(wT + (size_t)(k + 2) * kTimeDim + tid), x[k + 2], a2);
-            a3 = fmaf(__ldg(wT + (size_t)(k + 3) * kTimeDim + tid), x[k + 3], a3);
+#pragma unroll 16
+        for (int k = 0; k < kTimeDim / 4; ++k) {
+            const float4 wv = __ldg(row + k);
+            const float4 xv = reinterpret_cast<const float4*>(x)[k];
+            a0 = fmaf(wv.x, xv.x, a0); a1 = fmaf(wv.y, xv.y, a1); a2 = fmaf(wv.z, xv.z, a2); a3 = fmaf(wv.w, xv.w, a3);
         }
         return (a0 + a1) + (a2 + a3);
     };

@@ -136,8 +136,7 @@ class B200DiT(nn.Module):
         te = "time_embedder.timestep_embedder."
         for n, k in (("te_w1", "linear_1.weight"), ("te_b1", "linear_1.bias"), ("te_w2", "linear_2.weight"),
                      ("te_b2", "linear_2.bias")):
-            # the two 256x256 weights are handed over transposed ([in][out]): coalesced for the thread-per-output kernel
-            P[n] = (sd[te + k].t() if sd[te + k].dim() == 2 else sd[te + k]).contiguous().to(dev)
+            P[n] = sd[te + k].contiguous()
         # every AdaLayerNormZero.linear of the model, concatenated along the output dimension
         mods_w, mods_b, offs, off = [], [], {}, 0
         for stack, i, c in self._blocks_in_order():
