@@ -187,6 +187,8 @@ class DiffusionSampler:
         self.x_hat, self.x_den, self.aligned = (torch.empty_like(self.x_next) for _ in range(3))
         self.t_hat_dev = torch.empty(self.B, dtype=torch.float32, device=dev)
         self.last_used = None
+        self._sched_cache: Dict[int, tuple] = {}
+        self._sched_floats: Dict[int, tuple] = {}
 
     def begin(self) -> torch.Tensor:
         """x_0 = sigma_0 * N(0,1)   (prepare_solver, model.py:148)."""
@@ -194,7 +196,15 @@ class DiffusionSampler:
         return self.x_next
 
     def schedule(self, i: int):
-        """Host-side scalars of step i: (t_cur, t_next, t_hat, stochastic, noise_scale), model.py:213-220."""
+        """Host-side scalars of step i: (t_cur, t_next, t_hat, stochastic, noise_scale), model.py:213-220.
+        Computed once per step index (a handful of 0-dim CPU tensor ops = tens of microseconds of host time that the
+        end-to-end path, which synchronises every step, would otherwise pay on every call)."""
+        hit = self._sched_cache.get(i)
+        if hit is None:
+            hit = self._sched_cache[i] = self._schedule(i)
+        return hit
+
+    def _schedule(self, i: int):
         t_cur, t_next = self.sigmas[i], self.sigmas[i + 1]
         stochastic = bool(t_cur > self.gamma_min)
         if stochastic:
@@ -215,8 +225,13 @@ class DiffusionSampler:
     def step(self, i: int, randoms=None, teacher_x_hat: Optional[torch.Tensor] = None) -> torch.Tensor:
         """One iteration of the loop at schedule index i; returns (and stores) x_next."""
         t_cur, t_next, t_hat, stochastic, noise_scale = self.schedule(i)
+        fl = self._sched_floats.get(i)
+        if fl is None:       # python floats of the step's scalars + the two branch conditions, computed once per index
+            thr = self.gamma_min * self.mmff_factor
+            fl = self._sched_floats[i] = (float(t_hat), float(t_next), bool(t_cur > thr), bool(t_cur <= thr))
+        t_hat_f, t_next_f, early, late = fl
         u4, trans, noise = randoms if randoms is not None else self.draw(i)
-        self.t_hat_dev.fill_(float(t_hat))
+        self.t_hat_dev.fill_(t_hat_f)
         centre_augment_noise(self.x_next, self.x_exists, u4, trans, noise, self.lam, noise_scale, out=self.x_hat)
         if teacher_x_hat is not None:
             self.x_hat.copy_(teacher_x_hat)
@@ -226,26 +241,26 @@ class DiffusionSampler:
             self.dit.denoise(self.x_hat, self.t_hat_dev, out=self.x_den)
         self.last_used = None
         physics = False
-        if self.align_ref_pos and bool(t_cur > self.gamma_min * self.mmff_factor):
+        if self.align_ref_pos and early:
             if self.ref_mol_poses is not None:
                 _, self.last_used = template_select(self.x_den, self.lig_idx, self.ref_dist, self.ref_mol_poses,
                                                     self.batch_ref_pos)
             weighted_rigid_align(self.x_den, self.x_exists, self.batch_ref_pos, self.weights, out=self.aligned)
             physics = True
-        elif self.physics_field is not None and bool(t_cur <= self.gamma_min * self.mmff_factor):
+        elif self.physics_field is not None and late:
             # model.py:252-261 with get_next_step_pos replaced by mmff_iters descent steps on the pair energy (GPU)
             x_ref = self.physics_field.descend(self.x_den, iters=self.mmff_iters, step=self.physics_step,
                                                gmax=self.physics_gmax)
             weighted_rigid_align(self.x_den, self.x_exists, x_ref, self.weights, out=self.aligned)
             physics = True
-        elif self.mmff_fn is not None and bool(t_cur <= self.gamma_min * self.mmff_factor):
+        elif self.mmff_fn is not None and late:
             x_ref = self.x_den.clone()
             x_ref[:, self.is_ligand_atom] = self.mmff_fn(self.x_den[:, self.is_ligand_atom])
             weighted_rigid_align(self.x_den, self.x_exists, x_ref, self.weights, out=self.aligned)
             physics = True
         eta = self.eta_s if stochastic else self.eta_d
         x_new = torch.empty_like(self.x_next)
-        euler_update(self.x_hat, self.x_den, self.t_hat_dev, float(t_next), eta, self.aligned if physics else None,
+        euler_update(self.x_hat, self.x_den, self.t_hat_dev, t_next_f, eta, self.aligned if physics else None,
                      self.weights if physics else None, out=x_new)
         self.x_next = x_new
         return x_new
