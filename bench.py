@@ -124,12 +124,12 @@ def cpu_oracle_rate(n_calls, B_cpu, threads):
 
 def run_reference(args, rank):
     """--impl reference: the reference's CPU implementation of the step (oracle port; /root/reference does not
-    exist on the GPU box), all host threads, bounded sample B=4 per step."""
+    exist on the GPU box), all host threads, bounded sample B=8 per step."""
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    B_cpu = 4
-    n = max(1, min(args.steps, 8))
+    B_cpu = 8
+    n = max(1, min(args.steps, 12))
     rate, sec = cpu_oracle_rate(n, B_cpu, threads)
     sample = f"{n} timed steps (+1 warm-up) of B={B_cpu} samples at Nt={NT}/Na={NA}, fp32 PyTorch CPU, {threads} threads"
     print(json.dumps({
@@ -326,9 +326,9 @@ def main():
     }
     if not args.no_cpu_baseline and world == 1:
         threads = os.cpu_count() or 1
-        rate, sec = cpu_oracle_rate(3, 4, threads)
+        rate, sec = cpu_oracle_rate(10, 8, threads)       # ~10 s of CPU work: a bounded sample of the same workload
         out["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-                               "sample": f"3 timed steps (+1 warm-up) of B=4 samples at Nt={NT}/Na={NA}, fp32 PyTorch CPU "
+                               "sample": f"10 timed steps (+1 warm-up) of B=8 samples at Nt={NT}/Na={NA}, fp32 PyTorch CPU "
                                          f"oracle (bit-identical to the reference on CPU), {sec:.2f} s/step"}
     print(json.dumps(out))
     if world > 1:
