@@ -1,8 +1,12 @@
 #!/bin/bash
-# Builds debug variants of the library (gemm_umma.cu compile switches) as separate .so files -- run HERE (needs nvcc).
+# Builds debug variants of the library as separate .so files under build/dbg -- run HERE (needs nvcc).
+#   tools/gemm_variants.sh NO_EPI NO_STORE        -> -DPDK_DBG_NO_EPI, -DPDK_DBG_NO_STORE   (gemm_umma.cu)
+#   tools/gemm_variants.sh T_NOLN T_NOHID T_NOFINAL                                         (transition_umma.cu)
 cd "$(dirname "$0")/../physdock_b200/csrc"
 SRC="gemm_umma.cu transition_umma.cu tmap.cu attention_umma.cu pairbias.cu glue.cu coords.cu physics.cu capi.cu"
-for v in NO_STORE NO_EPI NO_TMAWAIT; do
-  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -shared -DPDK_DBG_$v -o /root/repo/build/dbg/libpdk_$v.so $SRC &
+mkdir -p ../../build/dbg
+for v in "$@"; do
+  case $v in T_*) def=PDK_$v ;; *) def=PDK_DBG_$v ;; esac
+  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -shared -D$def -o ../../build/dbg/libpdk_$v.so $SRC &
 done
-wait; ls -la /root/repo/build/dbg/libpdk_*.so
+wait; ls -la ../../build/dbg/
