@@ -24,11 +24,35 @@ int fail_msg(const char* where, const char* msg) {
     g_err = std::string(where) + ": " + msg;
     return -1;
 }
+#ifdef PDK_DBG_SKIP
+// Debug builds only (tools/gemm_variants.sh SKIP): PDK_SKIP="adaln,time_embed,..." drops the launches whose label contains one
+// of the words, to measure the upper bound of fusing / removing them (results are then wrong by construction).
+inline bool dbg_skip(const char* where) {
+    static const char* list = getenv("PDK_SKIP");
+    if (!list) return false;
+    std::string l(list), w(where);
+    size_t a = 0;
+    while (a <= l.size()) {
+        size_t b = l.find(',', a);
+        if (b == std::string::npos) b = l.size();
+        if (b > a && w.find(l.substr(a, b - a)) != std::string::npos) return true;
+        a = b + 1;
+    }
+    return false;
+}
+#define PDK_TRY(where, expr)                          \
+    do {                                              \
+        if (dbg_skip(where)) break;                   \
+        cudaError_t _e = (expr);                      \
+        if (_e != cudaSuccess) return fail(where, _e); \
+    } while (0)
+#else
 #define PDK_TRY(where, expr)                          \
     do {                                              \
         cudaError_t _e = (expr);                      \
         if (_e != cudaSuccess) return fail(where, _e); \
     } while (0)
+#endif
 
 inline int64_t pad128(int64_t n) { return (n + 127) / 128 * 128; }
 inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
