@@ -91,6 +91,13 @@ def load(path: Optional[str] = None) -> C.CDLL:
     if _lib is not None and path is None:
         return _lib
     p = path or os.environ.get("PHYSDOCK_B200_LIB", LIB_PATH)
+    if not os.path.exists(p) and p == LIB_PATH:
+        try:                        # a fresh checkout: compile the CUDA library in-tree once (nvcc, ~30 s)
+            from .build import build_library
+            build_library()
+        except Exception as e:      # noqa: BLE001 -- reported below; there is nothing to fall back to
+            raise PdkError(f"{p} not found and building it failed ({e}); "
+                           "there is no CPU or PyTorch fallback for the sampling step") from e
     if not os.path.exists(p):
         raise PdkError(f"{p} not found: build it with `python -m physdock_b200.build` "
                        "(there is no CPU or PyTorch fallback for the sampling step)")
