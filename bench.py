@@ -275,10 +275,15 @@ def main():
     barrier()
     barrier()
     e0.record()
+    # every step: H2D of x and of the step's randoms, the step, D2H of x_next, host sync.  The randoms of step i+1 are
+    # uploaded (copy stream) while step i computes; the result buffer of step i is the input buffer of step i+1.
+    up = smp.upload_randoms(W % SCHED_STEPS, u4_h, tr_h, nz_h)
     for i in range(K):
-        smp.step_from_host((W + i) % SCHED_STEPS, x_h, u4_h, tr_h, nz_h, out_h)
+        smp.step_from_host((W + i) % SCHED_STEPS, x_h, u4_h, tr_h, nz_h, out_h, uploaded=up)
+        if i + 1 < K:
+            up = smp.upload_randoms((W + i + 1) % SCHED_STEPS, u4_h, tr_h, nz_h)
         torch.cuda.current_stream().synchronize()        # the caller consumes x_next on the host every step
-        x_h.copy_(out_h)
+        x_h, out_h = out_h, x_h
     e1.record()
     barrier()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))

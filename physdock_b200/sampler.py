@@ -188,6 +188,7 @@ class DiffusionSampler:
         self.t_hat_dev = torch.empty(self.B, dtype=torch.float32, device=dev)
         self.last_used = None
         self._sched_cache: Dict[int, tuple] = {}
+        self._copy_stream = None
         self._sched_floats: Dict[int, tuple] = {}
 
     def begin(self) -> torch.Tensor:
@@ -265,13 +266,32 @@ class DiffusionSampler:
         self.x_next = x_new
         return x_new
 
-    def step_from_host(self, i: int, x_host: torch.Tensor, u4_host, trans_host, noise_host, out_host: torch.Tensor):
+    def upload_randoms(self, i: int, u4_host, trans_host, noise_host):
+        """H2D of step i's random tensors (pinned host memory) on a separate copy stream, so that it overlaps the
+        previous step's kernels; returns the device tensors and the event the compute stream must wait for."""
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.dev)
+        with torch.cuda.stream(self._copy_stream):
+            u4 = u4_host.to(self.dev, non_blocking=True)
+            trans = trans_host.to(self.dev, non_blocking=True)
+            noise = noise_host.to(self.dev, non_blocking=True) if self.schedule(i)[3] else None
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+        return u4, trans, noise, ev
+
+    def step_from_host(self, i: int, x_host: torch.Tensor, u4_host, trans_host, noise_host, out_host: torch.Tensor,
+                       uploaded=None):
         """Same step with every per-step input coming from pinned host memory and the result read back
-        (bench.py's end-to-end leg): H2D(x, randoms) -> step -> D2H(x_next)."""
+        (bench.py's end-to-end leg): H2D(x, randoms) -> step -> D2H(x_next).  `uploaded` = the result of an earlier
+        `upload_randoms(i, ...)` (the randoms do not depend on the previous step, only x does)."""
         self.x_next.copy_(x_host, non_blocking=True)
-        u4 = u4_host.to(self.dev, non_blocking=True)
-        trans = trans_host.to(self.dev, non_blocking=True)
-        noise = noise_host.to(self.dev, non_blocking=True) if self.schedule(i)[3] else None
+        if uploaded is None:
+            uploaded = self.upload_randoms(i, u4_host, trans_host, noise_host)
+        u4, trans, noise, ev = uploaded
+        torch.cuda.current_stream(self.dev).wait_event(ev)
+        for t in (u4, trans, noise):
+            if t is not None:
+                t.record_stream(torch.cuda.current_stream(self.dev))
         x = self.step(i, randoms=(u4, trans, noise))
         out_host.copy_(x, non_blocking=True)
         return out_host
