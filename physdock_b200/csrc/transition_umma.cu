@@ -13,9 +13,12 @@
 //   GEMM 2      : acc2 (TMEM) += H_j W2[:, 64j:64j+64]^T        -- the hidden activations never leave the SM
 //   final       : x += acc2 * gate  (whole 128-byte rows staged in the then-free A region, 4 rows x 128 B per store
 //                 instruction, residual prefetched); afterwards the same warps build the A operand of the next tile
-// Warps: 0 = TMA producer (weights only: starts before the previous kernel has finished, PDL), 1 = MMA issuer,
-// 2-17 = LN / epilogue warps (thread = one row x one 32-column chunk).  The weight tiles stream through a 3-stage ring
-// in exactly the order the MMA warp consumes them (G1_0, G1_1, G2_0, G1_2, G2_1, ...).
+// Warps: 0 = TMA producer (weights), 1 = MMA issuer, 2-17 = LN / epilogue warps (thread = one row x one 32-column
+// chunk).  The weight tiles stream through a 4-stage ring in exactly the order the MMA warp consumes them (G1_0, G1_1,
+// G2_0, G1_2, G2_1, ...); one hidden-tile buffer is enough (the epilogue of block j writes it while GEMM 1 of block j+1
+// runs; a second buffer with a 3-stage ring measured the same, -DPDK_TRANS_H2).
+// Where the time goes (debug switches -DPDK_T_NOLN / NOHID / NOFINAL, tools/gemm_variants.sh): 35.5 us per launch at
+// B=16 / Na=2048 = MMAs + loads 23 us + LayerNorm math 7.6 us + final epilogue 5 us; the hidden epilogues are free.
 #include "common.cuh"
 #include "kernels.h"
 #include "umma.cuh"
