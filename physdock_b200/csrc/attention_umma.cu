@@ -16,10 +16,11 @@
 //   warp 17 QK issuer      : S_g = Q_g K^T   (SS, M128 N64 K16 x 2 slices x 3 split products) into TMEM buffer g
 //   warp 18 PV issuer      : O_g += P_g V    (TS: P from TMEM, V MN-major from smem; 4 slices x 3 products)
 //                            Two issuing warps because one warp's serialized waits/commits left the tensor pipe
-//                            idle ~40% of the time (profiles/r01_attention_timeline.txt); QK(j,g) is ordered after
+//                            idle ~40% of the time; QK(j,g) is ordered after
 //                            PV(j-1,g) through the pv_done barrier (S and P share a TMEM buffer).
 //   warps 4g .. 4g+3      : softmax warpgroup of sample g (FOUR warpgroups; with two, each serving two samples, the
-//                            softmax warps were busy 87% of the time and set the pace: profiles/r01_attention_timeline.txt).
+//                            softmax warps were busy 87% of the time and set the pace; now they wait ~1000 cycles per unit for S:
+//                            profiles/r01_attention_timeline.txt).
 //                            Thread = one query row: reads its 64 scores with tcgen05.ld, adds the bias row, row max /
 //                            exp2 / row sum entirely in registers (no shuffles), splits P into fp16 hi/lo and writes it
 //                            back over S with tcgen05.st (S and P alias) in 16-column pieces so that the thread stays

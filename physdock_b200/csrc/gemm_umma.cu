@@ -16,8 +16,8 @@
 //        launch / two-CTA handshakes, so they stay on the single-CTA tiling.
 //   single CTA: 128 x 128 tiles.
 // Tiles are walked n-fastest so concurrently running CTAs share the A tile in L2.  Roles:
-//   warp 0   : TMA producer: 4 plane tiles [128 rows x 64 halves] per stage, SWIZZLE_128B, 3-stage ring (192 KB)
-//              that runs ahead across tile boundaries
+//   warp 0   : TMA producer: 4 plane tiles [128 rows x 64 halves] per stage, SWIZZLE_128B, ring of 3 stages (single CTA,
+//              64 KB each) / 4 stages (pair, 48 KB each), one fewer with WIDE epilogue staging; runs ahead across tiles
 //   warp 1   : TMEM allocator + MMA issuer: 12 x tcgen05.mma.kind::f16 M128 N128 K16 per stage into one of TWO
 //              128-column accumulators, so the epilogue of tile i overlaps the main loop of tile i+1
 //   warps 2-17: epilogue (four warps per TMEM lane quarter, one 32-column chunk each).  A THREAD owns one output
