@@ -53,14 +53,17 @@ PDK_DEV void mma_f16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_
 // evaluated on the tensor cores as a_hi*b_hi + a_hi*b_lo + a_lo*b_hi with fp32 accumulation, which
 // tools/precision_probe.py shows is indistinguishable from fp32 at the 1e-3 Angstrom parity budget.
 constexpr float kHalfMax = 65504.f;
+// Values beyond +-65504 saturate (cvt.satfinite: the documented limit of the format); in range the result is exactly
+// hi = fp16(x), lo = fp16(x - hi).  6 instructions per pair (the explicit fminf/fmaxf clamp cost 4 more).
 PDK_DEV void split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
-    x0 = fminf(fmaxf(x0, -kHalfMax), kHalfMax);
-    x1 = fminf(fmaxf(x1, -kHalfMax), kHalfMax);
-    __half2 h = __floats2half2_rn(x0, x1);
-    float2 hf = __half22float2(h);
-    __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
-    hi = *reinterpret_cast<uint32_t*>(&h);
-    lo = *reinterpret_cast<uint32_t*>(&l);
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+    const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(x1 - hf.y), "f"(x0 - hf.x));
+}
+// 1/sqrt(x) from MUFU rsqrt + one Newton step (relative error ~1e-7; the IEEE sqrt + divide pair is ~25 instructions)
+PDK_DEV float inv_sqrt(float x) {
+    const float y = rsqrtf(x);
+    return y * fmaf(-0.5f * x * y, y, 1.5f);
 }
 // same, for values known to lie in [0, 1] (softmax probabilities)
 PDK_DEV void split2_unit(float x0, float x1, uint32_t& hi, uint32_t& lo) {

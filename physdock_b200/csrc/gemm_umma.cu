@@ -361,7 +361,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant_
                     float ss = 0.f;
 #pragma unroll
                     for (int i = 0; i < 32; ++i) ss = fmaf(v[i], v[i], ss);
-                    const float inv = (1.0f / sqrtf(ss * (1.0f / kHeadDim) + p.rms_eps)) * (which == 0 ? p.q_scale : 1.0f);
+                    const float inv = (inv_sqrt(ss * (1.0f / kHeadDim) + p.rms_eps)) * (which == 0 ? p.q_scale : 1.0f);
                     const float* gain = which == 0 ? p.norm_q : p.norm_k;
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {

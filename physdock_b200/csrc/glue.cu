@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(256) adaln_kernel(const float* __restrict__ x,
         v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
         sq += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
     }
-    const float rstd = 1.0f / sqrtf(warp_sum(sq) * (1.f / C) + eps);
+    const float rstd = inv_sqrt(warp_sum(sq) * (1.f / C) + eps);
     const float* shift = mod + (size_t)(row / S_pad) * mod_stride + mod_off;
     const float* scale = shift + C;
 #pragma unroll
@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(256) denoise_out_kernel(const float* __restric
     float4 v = reinterpret_cast<const float4*>(ba + ((size_t)b * S_pad + s) * 128)[lane];
     const float mean = warp_sum(v.x + v.y + v.z + v.w) * (1.f / 128.f);
     v.x -= mean; v.y -= mean; v.z -= mean; v.w -= mean;
-    const float rstd = 1.0f / sqrtf(warp_sum(v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w) * (1.f / 128.f) + eps);
+    const float rstd = inv_sqrt(warp_sum(v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w) * (1.f / 128.f) + eps);
     const float4 g = reinterpret_cast<const float4*>(ln_w)[lane];
     const float4 be = reinterpret_cast<const float4*>(ln_b)[lane];
     const float y0 = v.x * rstd * g.x + be.x, y1 = v.y * rstd * g.y + be.y;

@@ -212,7 +212,7 @@ transition_umma_kernel(const __grid_constant__ CUtensorMap mW13h, const __grid_c
 #endif
                 const float mean = warp_sum(v[i].x + v[i].y + v[i].z + v[i].w) * (1.f / TC);
                 v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
-                const float rstd = 1.0f / sqrtf(warp_sum(v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w) * (1.f / TC) + p.eps);
+                const float rstd = inv_sqrt(warp_sum(v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w) * (1.f / TC) + p.eps);
                 uint2 hi, lo;
                 split2(v[i].x * rstd * (1.f + sc.x) + sh.x, v[i].y * rstd * (1.f + sc.y) + sh.y, hi.x, lo.x);
                 split2(v[i].z * rstd * (1.f + sc.z) + sh.z, v[i].w * rstd * (1.f + sc.w) + sh.w, hi.y, lo.y);
