@@ -98,6 +98,33 @@ PDK_DEV double warp_sum(double v) {
 }
 
 
+// Sums of EIGHT per-lane values over the warp at once: after three exchange steps each lane holds one row's partial sum
+// (17 shuffles instead of the 40 of eight separate butterflies); every lane ends with all eight totals.
+PDK_DEV void warp_sum8(float (&s)[8]) {
+    const unsigned lane = threadIdx.x & 31u;
+    const bool b16 = lane & 16u, b8 = lane & 8u, b4 = lane & 4u;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float send = b16 ? s[i] : s[i + 4], keep = b16 ? s[i + 4] : s[i];
+        s[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float send = b8 ? s[i] : s[i + 2], keep = b8 ? s[i + 2] : s[i];
+        s[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    {
+        const float send = b4 ? s[0] : s[1], keep = b4 ? s[1] : s[0];
+        s[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    s[0] += __shfl_xor_sync(0xffffffffu, s[0], 2);
+    s[0] += __shfl_xor_sync(0xffffffffu, s[0], 1);
+    // s[0] is now the total of row 4*[lane&16] + 2*[lane&8] + [lane&4]
+    const float t = s[0];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] = __shfl_sync(0xffffffffu, t, ((i >> 2) & 1) * 16 + ((i >> 1) & 1) * 8 + (i & 1) * 4);
+}
+
 #define PDK_LAUNCH_CHECK(expr)                 \
     do {                                       \
         cudaError_t e_ = (expr);               \

@@ -358,9 +358,13 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant_
                 const int head = (col & (p.c - 1)) / kHeadDim;
                 const int H = p.c / kHeadDim;
                 if (which < 2) {    // per-head RMSNorm (rms_norm.py:14-19); q additionally carries log2e/sqrt(32)
-                    float ss = 0.f;
+                    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;      // four partial sums: a 32-deep FMA chain is pure latency
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) ss = fmaf(v[i], v[i], ss);
+                    for (int i = 0; i < 32; i += 4) {
+                        s0 = fmaf(v[i], v[i], s0); s1 = fmaf(v[i + 1], v[i + 1], s1);
+                        s2 = fmaf(v[i + 2], v[i + 2], s2); s3 = fmaf(v[i + 3], v[i + 3], s3);
+                    }
+                    const float ss = (s0 + s1) + (s2 + s3);
                     const float inv = (inv_sqrt(ss * (1.0f / kHeadDim) + p.rms_eps)) * (which == 0 ? p.q_scale : 1.0f);
                     const float* gain = which == 0 ? p.norm_q : p.norm_k;
 #pragma unroll

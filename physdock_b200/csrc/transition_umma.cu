@@ -200,19 +200,29 @@ transition_umma_kernel(const __grid_constant__ CUtensorMap mW13h, const __grid_c
             const float* shift = p.mod + (size_t)(m0 / p.rows_per_sample) * p.mod_stride + p.mod_off;
             const float4 sh = *reinterpret_cast<const float4*>(shift + lane * 4);
             const float4 sc = *reinterpret_cast<const float4*>(shift + TC + lane * 4);
+#ifdef PDK_T_NOLN
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int row = ew * 8 + i;
-#ifdef PDK_T_NOLN
-                {
-                    const uint32_t off = (uint32_t)((lane >> 4) * PT + row * 128 + (((((lane & 15) >> 1)) ^ (row & 7)) << 4) + (lane & 1) * 8);
-                    asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(sm + OFF_A + off), "r"(__float_as_uint(v[i].x)), "r"(__float_as_uint(v[i].y)) : "memory");
-                    continue;
-                }
-#endif
-                const float mean = warp_sum(v[i].x + v[i].y + v[i].z + v[i].w) * (1.f / TC);
+                const uint32_t off = (uint32_t)((lane >> 4) * PT + row * 128 + (((((lane & 15) >> 1)) ^ (row & 7)) << 4) + (lane & 1) * 8);
+                asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(sm + OFF_A + off), "r"(__float_as_uint(v[i].x)), "r"(__float_as_uint(v[i].y)) : "memory");
+            }
+#else
+            float red[8];                             // the 8 rows' reductions go through ONE multi-value butterfly
+#pragma unroll
+            for (int i = 0; i < 8; ++i) red[i] = (v[i].x + v[i].y) + (v[i].z + v[i].w);
+            warp_sum8(red);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float mean = red[i] * (1.f / TC);
                 v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
-                const float rstd = inv_sqrt(warp_sum(v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w) * (1.f / TC) + p.eps);
+                red[i] = fmaf(v[i].x, v[i].x, v[i].y * v[i].y) + fmaf(v[i].z, v[i].z, v[i].w * v[i].w);
+            }
+            warp_sum8(red);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int row = ew * 8 + i;
+                const float rstd = inv_sqrt(red[i] * (1.f / TC) + p.eps);
                 uint2 hi, lo;
                 split2(v[i].x * rstd * (1.f + sc.x) + sh.x, v[i].y * rstd * (1.f + sc.y) + sh.y, hi.x, lo.x);
                 split2(v[i].z * rstd * (1.f + sc.z) + sh.z, v[i].w * rstd * (1.f + sc.w) + sh.w, hi.y, lo.y);
@@ -221,6 +231,7 @@ transition_umma_kernel(const __grid_constant__ CUtensorMap mW13h, const __grid_c
                 asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(sm + OFF_A + off), "r"(hi.x), "r"(hi.y) : "memory");
                 asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(sm + OFF_A + 2 * PT + off), "r"(lo.x), "r"(lo.y) : "memory");
             }
+#endif
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&bars.a_ready));
