@@ -124,6 +124,12 @@ int pdk_template_select(const float* x_den, const int32_t* lig_idx, const float*
 int pdk_rigid_align(const float* x_den, const float* x_exists, const float* x_gt, int gt_batched, const float* w,
                     float* aligned, int64_t B, int64_t Na, void* stream);
 
+/* Host only: the attention kernel's CTA work list for B samples, H heads, n_qtiles 128-row query tiles on n_sms SMs.
+ * out[i] = head | q_tile << 8 | first_sample << 16 | n_samples << 24 (n_samples <= 4), ordered by decreasing n_samples;
+ * every (head, q tile, sample) appears exactly once.  Returns the number of entries, -1 if the shape needs more than one
+ * launch (the library then splits the samples), -2 if cap is too small. */
+int64_t pdk_attention_work_list(int64_t B, int64_t H, int64_t n_qtiles, int64_t n_sms, uint32_t* out, int64_t cap);
+
 /* Pose ranking (redocking.py:391): dist[S,S] (fp64) = sqrt(mean over the n ligand atoms of |pose_s - pose_t|^2). */
 int pdk_pairwise_rmsd(const float* poses, double* dist, int64_t S, int64_t n, void* stream);
 

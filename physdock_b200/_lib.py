@@ -59,6 +59,7 @@ PROTOTYPES = {
     "pdk_euler_update": (_int, [_vp] * 5 + [_f32, _f32, _vp, _i64, _i64, _vp]),
     "pdk_template_select": (_int, [_vp] * 7 + [_i64] * 4 + [_vp]),
     "pdk_rigid_align": (_int, [_vp, _vp, _vp, _int, _vp, _vp, _i64, _i64, _vp]),
+    "pdk_attention_work_list": (_i64, [_i64, _i64, _i64, _i64, _vp, _i64]),
     "pdk_pairwise_rmsd": (_int, [_vp, _vp, _i64, _i64, _vp]),
     "pdk_pair_energy_grad": (_int, [_vp] * 7 + [_i64, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _vp, _vp, _vp, _i64, _i64,
                                     _vp]),

@@ -484,6 +484,15 @@ const WorkList* get_work_list(int B, int H, int QT, int sms) {
 
 }  // namespace
 
+// Host-only view of the work list (C ABI: pdk_attention_work_list; checked without a GPU in tests/test_cabi.py)
+int attention_work_list(int B, int H, int QT, int sms, uint32_t* out, int cap) {
+    const WorkList* wl = get_work_list(B, H, QT, sms);
+    if (wl == nullptr) return -1;
+    if (wl->n > cap) return -2;
+    for (int i = 0; i < wl->n; ++i) out[i] = wl->w.e[i];
+    return wl->n;
+}
+
 cudaError_t launch_attention(const AttnArgs& a_in, cudaStream_t st) {
     AttnArgs a = a_in;
     a.trace = g_trace;

@@ -367,6 +367,11 @@ int pdk_template_select(const float* x_den, const int32_t* lig_idx, const float*
     return 0;
 }
 
+int64_t pdk_attention_work_list(int64_t B, int64_t H, int64_t n_qtiles, int64_t n_sms, uint32_t* out, int64_t cap) {
+    if (!out || B <= 0 || H <= 0 || n_qtiles <= 0 || n_sms <= 0) { fail_msg("pdk_attention_work_list", "bad argument"); return -3; }
+    return attention_work_list((int)B, (int)H, (int)n_qtiles, (int)n_sms, out, (int)cap);
+}
+
 int pdk_pairwise_rmsd(const float* poses, double* dist, int64_t n_poses, int64_t n, void* stream) {
     if (!poses || !dist) return fail_msg("pdk_pairwise_rmsd", "null argument");
     PDK_TRY("pairwise_rmsd", launch_pairwise_rmsd(poses, dist, (int)n_poses, (int)n, S(stream)));

@@ -59,6 +59,8 @@ struct AttnArgs {
     long long* trace;   // debug only: per-unit clock64 stamps of CTA (0,0,0); nullptr in production
 };
 cudaError_t launch_attention(const AttnArgs& a, cudaStream_t st);
+// entries (head | q tile << 8 | first sample << 16 | samples << 24) of the balanced work list; -1: does not fit one launch
+int attention_work_list(int B, int H, int QT, int sms, uint32_t* out, int cap);
 void set_attention_trace(long long* buf);   // debug hook used by tools/trace_attention.py
 
 // ----------------------------------------------------------------------------- pair-bias prepass

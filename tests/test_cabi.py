@@ -73,3 +73,33 @@ def test_module_mirrors_reference_state_dict():
         assert list(sd.keys()) == list(dit_param_shapes(d).keys())
         assert all(tuple(sd[k].shape) == s for k, s in dit_param_shapes(d).items())
     assert sum(p.numel() for p in B200DiT().parameters()) == 50772160      # 50.77 M
+
+
+@pytest.mark.parametrize("B,H,QT", [(16, 4, 16), (16, 16, 2), (1, 4, 1), (5, 4, 2), (7, 16, 1), (40, 4, 3), (48, 16, 3), (3, 4, 24)])
+def test_attention_work_list_covers_every_sample_once(lib, B, H, QT):
+    """Host logic of attention_umma.cu: balanced sample groups, largest first, every (head, q tile, sample) exactly once."""
+    import ctypes as C
+    buf = (C.c_uint32 * 800)()
+    n = lib.pdk_attention_work_list(B, H, QT, 148, buf, 800)
+    assert 0 < n <= 800
+    seen = set()
+    sizes = []
+    for i in range(n):
+        e = buf[i]
+        h, qt, b0, ng = e & 0xff, (e >> 8) & 0xff, (e >> 16) & 0xff, e >> 24
+        assert 1 <= ng <= 4 and h < H and qt < QT and b0 + ng <= B
+        sizes.append(ng)
+        for b in range(b0, b0 + ng):
+            assert (h, qt, b) not in seen
+            seen.add((h, qt, b))
+    assert len(seen) == B * H * QT
+    assert sizes == sorted(sizes, reverse=True)
+    if (B, H, QT) == (16, 4, 16):       # the benchmark shape: one 4-sample and one 3-sample CTA per SM
+        assert n == 292 and sizes.count(4) == 148 and sizes.count(3) == 144
+
+
+def test_attention_work_list_limits(lib):
+    import ctypes as C
+    buf = (C.c_uint32 * 800)()
+    assert lib.pdk_attention_work_list(64, 4, 24, 148, buf, 800) == -1      # 96 pairs x 17 groups: the library splits the samples
+    assert lib.pdk_attention_work_list(16, 4, 16, 148, buf, 10) == -2
