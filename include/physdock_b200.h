@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define PDK_ABI_VERSION 1
+#define PDK_ABI_VERSION 2
 
 int pdk_abi_version(void);
 const char* pdk_last_error(void);
@@ -99,6 +99,27 @@ int pdk_dit_denoise(pdk_dit* h, const float* x_hat, const float* t_hat, int64_t 
                     size_t workspace_bytes, float* x_denoised, void* stream);
 /* number of kernels one pdk_dit_denoise call enqueues (for bench.py's gpu_launches) */
 int64_t pdk_dit_launches_per_denoise(const pdk_dit* h);
+
+/* Conditioning hoisted out of the step.  Everything AF3DiT derives from t_hat alone -- precond scalars
+ * (transformers.py:219-221,229-230), TimestepEmbeddings (timestep_embeddings.py:156-166) and the 36
+ * AdaLayerNormZero.linear(SiLU(t)) modulations (adaptive_layer_norm_zero.py:19) -- depends only on the noise level,
+ * and the sampler (model.py:211-221) uses ONE noise level per step for all samples, known from the schedule before the
+ * loop starts.  pdk_dit_conditioning computes the rows for n noise levels at once (2 launches):
+ *   table[i, 0 .. n_mod)            = modulation row of t_hat[i]
+ *   table[i, n_mod .. n_mod + 4)    = (c_in, c_skip, c_out, t_hat[i])
+ *   table[i, n_mod + 4 .. n_mod + 8) = reserved for the caller: (t_next, eta, -, -), read by the fused Euler update
+ * table is fp32 [pad_len(n), table_ld], table_ld >= pdk_dit_cond_width() and a multiple of 4; rows >= n are scratch. */
+int64_t pdk_dit_cond_width(const pdk_dit* h);
+int pdk_dit_conditioning_workspace_bytes(const pdk_dit* h, int64_t n, size_t* bytes);
+int pdk_dit_conditioning(pdk_dit* h, const float* t_hat, int64_t n, void* workspace, size_t workspace_bytes, float* table,
+                         int64_t table_ld, void* stream);
+/* pdk_dit_denoise with the conditioning rows given: sample b uses cond + b * cond_stride (cond_stride = 0: one row shared
+ * by all samples -- the sampler's case).  x_next != NULL additionally writes the physics-free Euler update
+ * x_next = x_hat + eta (t_next - t_hat) (x_hat - x_denoised) / t_hat  (model.py:263-264,278-281) from the same kernel
+ * that produces x_denoised, with (t_next, eta) taken from the row. */
+int pdk_dit_denoise_cond(pdk_dit* h, const float* x_hat, const float* cond, int64_t cond_stride, int64_t B, void* workspace,
+                         size_t workspace_bytes, float* x_denoised, float* x_next, void* stream);
+int64_t pdk_dit_launches_per_denoise_cond(const pdk_dit* h);
 
 /* ------------------------------------------------------------------------------------------------
  * Sampler-side coordinate / physics ops (PhysDock/models/model.py:211-281)

@@ -55,6 +55,11 @@ PROTOTYPES = {
     "pdk_dit_prepare_complex": (_int, [_vp] + [_vp] * 8 + [_i64, _i64, _vp, _vp, _vp]),
     "pdk_dit_denoise": (_int, [_vp, _vp, _vp, _i64, _vp, C.c_size_t, _vp, _vp]),
     "pdk_dit_launches_per_denoise": (_i64, [_vp]),
+    "pdk_dit_cond_width": (_i64, [_vp]),
+    "pdk_dit_conditioning_workspace_bytes": (_int, [_vp, _i64, C.POINTER(C.c_size_t)]),
+    "pdk_dit_conditioning": (_int, [_vp, _vp, _i64, _vp, C.c_size_t, _vp, _i64, _vp]),
+    "pdk_dit_denoise_cond": (_int, [_vp, _vp, _vp, _i64, _i64, _vp, C.c_size_t, _vp, _vp, _vp]),
+    "pdk_dit_launches_per_denoise_cond": (_i64, [_vp]),
     "pdk_centre_augment": (_int, [_vp] * 5 + [_f32, _f32, _f32, _vp, _i64, _i64, _vp]),
     "pdk_euler_update": (_int, [_vp] * 5 + [_f32, _f32, _vp, _i64, _i64, _vp]),
     "pdk_template_select": (_int, [_vp] * 7 + [_i64] * 4 + [_vp]),
@@ -83,6 +88,7 @@ PROTOTYPES = {
     "pdk_op_denoise_out": (_int, [_vp] * 7 + [_i64] * 4 + [_f32, _vp]),
 }
 
+ABI_VERSION = 2
 _lib: Optional[C.CDLL] = None
 
 
@@ -106,7 +112,7 @@ def load(path: Optional[str] = None) -> C.CDLL:
     for name, (res, args) in PROTOTYPES.items():
         fn = getattr(lib, name)        # AttributeError if the symbol is missing
         fn.restype, fn.argtypes = res, args
-    if lib.pdk_abi_version() != 1:
+    if lib.pdk_abi_version() != ABI_VERSION:
         raise PdkError("ABI version mismatch")
     if path is None:
         _lib = lib

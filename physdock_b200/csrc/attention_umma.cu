@@ -449,7 +449,7 @@ const WorkList* get_work_list(int B, int H, int QT, int sms) {
     if (H > 255 || QT > 255 || B > 255 || (long long)pairs * (k0 + 1) > kMaxWork) return nullptr;
     const Partition coarse = make_partition(B, k0);
     const Partition fine = (k0 + 1 <= B) ? make_partition(B, k0 + 1) : coarse;
-    static const bool no_balance = getenv("PDK_NO_ATTN_BALANCE") != nullptr;      // measurement switch
+    static const bool no_balance = measure_switch("PDK_NO_ATTN_BALANCE");
     const double fixed = 0.15;        // per-CTA prologue + epilogue in sample-units (one unit = all key tiles of one sample)
     int best_y = 0;
     double best = 1e30;
@@ -497,19 +497,13 @@ cudaError_t launch_attention(const AttnArgs& a_in, cudaStream_t st) {
     AttnArgs a = a_in;
     a.trace = g_trace;
     if (a.S_pad <= 0 || a.S_pad % BQ || a.c != a.H * D || a.B <= 0) return cudaErrorInvalidValue;
-    static bool configured = false;
-    static int num_sms = 0;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(attention_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-        if (e != cudaSuccess) return e;
-        int dev = 0;
-        if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
-        if ((e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
-        configured = true;
-    }
+    static PerDevice configured;
+    int num_sms = 0;
+    cudaError_t e;
+    if ((e = ensure_smem(configured, attention_umma_kernel, SMEM_BYTES)) != cudaSuccess) return e;
+    if ((e = device_sm_count(&num_sms)) != cudaSuccess) return e;
     const uint64_t rows = (uint64_t)a.B * a.H * a.S_pad;
     CUtensorMap mQ, mK, mV, mBias;
-    cudaError_t e;
     if ((e = get_tensor_map_f16(a.q, rows, 2 * D, 2 * D, BQ, 2 * D, 128, &mQ)) != cudaSuccess) return e;
     if ((e = get_tensor_map_f16(a.k, rows, 2 * D, 2 * D, BKV, 2 * D, 128, &mK)) != cudaSuccess) return e;
     if ((e = get_tensor_map_f16(a.v, rows, 2 * D, 2 * D, BKV, 2 * D, 128, &mV)) != cudaSuccess) return e;

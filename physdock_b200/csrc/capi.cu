@@ -100,7 +100,7 @@ Workspace carve(const pdk_dit& h, int64_t B, int64_t Sa, int64_t St, uint8_t* ba
     const size_t Ma = (size_t)B * Sa, Mt = (size_t)B * St;
     const size_t act = std::max(Ma * h.d.c_a, Mt * h.d.c_s);            // elements of the widest activation
     const size_t hid = std::max(Ma * h.d.hidden_a, Mt * h.d.hidden_s);
-    w.coef = (float*)take((size_t)B * 4 * 4);
+    w.coef = (float*)take((size_t)B * kCoefWidth * 4);
     const size_t Bp = (size_t)pad128(B);                    // the modulation GEMM runs on 128-row tiles
     w.tsilu = (float*)take((size_t)B * kTimeDim * 4);
     w.tsh = (__half*)take(Bp * kTimeDim * 2);
@@ -123,19 +123,20 @@ Workspace carve(const pdk_dit& h, int64_t B, int64_t Sa, int64_t St, uint8_t* ba
 constexpr int kLaunchesPerBlock = 7;
 constexpr int kLaunchesPerFusedBlock = 5;        // atom blocks: the transition is one kernel (transition_umma.cu)
 inline bool fused_transition_enabled() {
-    static const bool on = getenv("PDK_NO_FUSED_TRANSITION") == nullptr;      // measurement switch
+    static const bool on = !measure_switch("PDK_NO_FUSED_TRANSITION");
     return on;
 }
 
 // One DiTBlock (transformers.py:155-159): x += Attn(x); x += Transition(x).
-int run_block(const pdk_dit& h, const pdk_block_weights& bw, const Workspace& ws, float* x, int64_t B, int64_t Sp,
-              int c, int hidden, const float* bias, cudaStream_t st) {
+// `mod` = modulation rows (all AdaLN-Zero layers side by side), `nmod` = stride between the rows of consecutive samples
+// in floats (0: one row shared by every sample, the sampler's case: all samples of a step have the same noise level).
+int run_block(const pdk_dit& h, const pdk_block_weights& bw, const Workspace& ws, const float* mod, int nmod, float* x,
+              int64_t B, int64_t Sp, int c, int hidden, const float* bias, cudaStream_t st) {
     const int M = (int)(B * Sp);
     const int Hh = c / kHeadDim;
-    const int nmod = (int)h.d.n_mod;
     const float eps = (float)h.d.eps;
     // --- attention (attentions.py:240-265)
-    PDK_TRY("adaln(attn)", launch_adaln(x, ws.mod, nmod, (int)bw.mod_attn_off, ws.xh, ws.xl, (int)B, (int)Sp, c, eps, st));
+    PDK_TRY("adaln(attn)", launch_adaln(x, mod, nmod, (int)bw.mod_attn_off, ws.xh, ws.xl, (int)B, (int)Sp, c, eps, st));
     GemmArgs g{};
     g.Ah = ws.xh; g.Al = ws.xl; g.lda = c;
     g.Wh = H(bw.wqkv_h); g.Wl = H(bw.wqkv_l); g.ldw = c;
@@ -151,18 +152,18 @@ int run_block(const pdk_dit& h, const pdk_block_weights& bw, const Workspace& ws
     g.Wh = H(bw.wo_h); g.Wl = H(bw.wo_l); g.ldw = c;
     g.M = M; g.N = c; g.K = c;
     g.bias = bw.bo; g.out = x; g.ldo = c;
-    g.gate = ws.mod + bw.mod_attn_off + 2 * c; g.gate_stride = nmod; g.rows_per_sample = (int)Sp;
+    g.gate = mod + bw.mod_attn_off + 2 * c; g.gate_stride = nmod; g.rows_per_sample = (int)Sp;
     PDK_TRY("gemm(out)", launch_gemm(EPI_GATE_RESID, g, st));
     // --- transition (transitions.py:21-30)
     if (c == 128 && fused_transition_enabled()) {
         TransitionArgs ta{};
-        ta.x = x; ta.mod = ws.mod; ta.mod_stride = nmod; ta.mod_off = (int)bw.mod_ffn_off;
+        ta.x = x; ta.mod = mod; ta.mod_stride = nmod; ta.mod_off = (int)bw.mod_ffn_off;
         ta.w13h = H(bw.w13_h); ta.w13l = H(bw.w13_l); ta.w2h = H(bw.w2_h); ta.w2l = H(bw.w2_l);
         ta.M = M; ta.hidden = hidden; ta.rows_per_sample = (int)Sp; ta.eps = eps;
         PDK_TRY("transition(fused)", launch_transition_fused(ta, st));
         return 0;
     }
-    PDK_TRY("adaln(ffn)", launch_adaln(x, ws.mod, nmod, (int)bw.mod_ffn_off, ws.xh, ws.xl, (int)B, (int)Sp, c, eps, st));
+    PDK_TRY("adaln(ffn)", launch_adaln(x, mod, nmod, (int)bw.mod_ffn_off, ws.xh, ws.xl, (int)B, (int)Sp, c, eps, st));
     g = GemmArgs{};
     g.Ah = ws.xh; g.Al = ws.xl; g.lda = c;
     g.Wh = H(bw.w13_h); g.Wl = H(bw.w13_l); g.ldw = c;
@@ -174,7 +175,7 @@ int run_block(const pdk_dit& h, const pdk_block_weights& bw, const Workspace& ws
     g.Wh = H(bw.w2_h); g.Wl = H(bw.w2_l); g.ldw = hidden;
     g.M = M; g.N = c; g.K = hidden;
     g.out = x; g.ldo = c;
-    g.gate = ws.mod + bw.mod_ffn_off + 2 * c; g.gate_stride = nmod; g.rows_per_sample = (int)Sp;
+    g.gate = mod + bw.mod_ffn_off + 2 * c; g.gate_stride = nmod; g.rows_per_sample = (int)Sp;
     PDK_TRY("gemm(w2)", launch_gemm(EPI_GATE_RESID, g, st));
     return 0;
 }
@@ -184,8 +185,10 @@ int run_block(const pdk_dit& h, const pdk_block_weights& bw, const Workspace& ws
 extern "C" {
 
 int pdk_abi_version(void) { return PDK_ABI_VERSION; }
-// debug hook (not part of the public header): per-unit timeline of the attention kernel, see tools/trace_attention.py
+#ifdef PDK_MEASURE
+// measurement builds only (not in the public header): per-unit timeline of the attention kernel, tools/trace_attention.py
 void pdk_debug_attention_trace(void* buf) { set_attention_trace(reinterpret_cast<long long*>(buf)); }
+#endif
 const char* pdk_last_error(void) { return g_err.c_str(); }
 int64_t pdk_pad_len(int64_t n) { return pad128(n); }
 
@@ -265,38 +268,41 @@ int64_t pdk_dit_launches_per_denoise(const pdk_dit* h) {
     const int64_t per_atom_block = fused_transition_enabled() ? kLaunchesPerFusedBlock : kLaunchesPerBlock;
     return 3 + per_atom_block * 2 * h->d.n_atom_blocks + kLaunchesPerBlock * h->d.n_token_blocks + 3 + 3 + 1;
 }
+// pdk_dit_denoise_cond: the two conditioning launches are not part of the step
+int64_t pdk_dit_launches_per_denoise_cond(const pdk_dit* h) { return h ? pdk_dit_launches_per_denoise(h) - 2 : 0; }
 
-int pdk_dit_denoise(pdk_dit* h, const float* x_hat, const float* t_hat, int64_t B, void* workspace,
-                    size_t workspace_bytes, float* x_denoised, void* stream) {
-    if (!h || !h->prepared) return fail_msg("pdk_dit_denoise", "no prepared complex");
-    if (!x_hat || !t_hat || !workspace || !x_denoised || B <= 0) return fail_msg("pdk_dit_denoise", "bad argument");
+// time embedding + all AdaLN-Zero modulations for n noise levels: table rows [mod (n_mod) | coef (kCoefWidth)]
+static int run_conditioning(pdk_dit* h, const float* t_hat, int64_t n, __half* tsh, __half* tsl, float* table, int64_t table_ld,
+                            cudaStream_t st) {
+    const pdk_dit_dims& d = h->d;
+    // precond scalars + TimestepEmbeddings (transformers.py:218-226) ...
+    PDK_TRY("time_embed", launch_time_embed(t_hat, h->w.freq, h->w.te_w1, h->w.te_b1, h->w.te_w2, h->w.te_b2, (float)d.sigma_data,
+                                            nullptr, tsh, tsl, (int)pad128(n), table + d.n_mod, (int)table_ld, (int)n, st));
+    // ... and every AdaLayerNormZero.linear of the model as ONE tensor-core GEMM [pad128(n) x 256] x [n_mod x 256]^T
+    // (adaptive_layer_norm_zero.py:19, all 36 layers)
+    GemmArgs g{};
+    g.Ah = tsh; g.Al = tsl; g.lda = kTimeDim;
+    g.Wh = H(h->w.wmod_h); g.Wl = H(h->w.wmod_l); g.ldw = kTimeDim;
+    g.M = (int)pad128(n); g.N = (int)d.n_mod; g.K = kTimeDim;
+    g.bias = h->w.bmod; g.out = table; g.ldo = (int)table_ld;
+    PDK_TRY("gemm(mod)", launch_gemm(EPI_STORE, g, st));
+    return 0;
+}
+
+// AF3DiT.forward (transformers.py:235-262) given the conditioning rows.
+static int run_denoise(pdk_dit* h, const float* x_hat, const float* mod, int mod_stride, const float* coef, int coef_stride,
+                       int64_t B, const Workspace& ws, float* x_denoised, float* x_next, cudaStream_t st) {
     const pdk_dit_dims& d = h->d;
     const int64_t Sa = h->Sa, St = h->St;
-    Workspace ws = carve(*h, B, Sa, St, reinterpret_cast<uint8_t*>(workspace));
-    if (ws.bytes > workspace_bytes) return fail_msg("pdk_dit_denoise", "workspace too small");
-    cudaStream_t st = S(stream);
     const int ca = (int)d.c_a, cs = (int)d.c_s;
     const int Ha = h->H_a(), Hs = h->H_s();
     const int nA = (int)d.n_atom_blocks, nT = (int)d.n_token_blocks;
-
-    // precond (transformers.py:218-226) + all AdaLN-Zero modulations of this step
-    // ... as ONE tensor-core GEMM [pad128(B) x 256] x [n_mod x 256]^T (adaptive_layer_norm_zero.py:19, all 36 layers)
-    PDK_TRY("time_embed", launch_time_embed(t_hat, h->w.freq, h->w.te_w1, h->w.te_b1, h->w.te_w2, h->w.te_b2,
-                                            (float)d.sigma_data, nullptr, ws.tsh, ws.tsl, (int)pad128(B), ws.coef, (int)B, st));
-    {
-        GemmArgs g{};
-        g.Ah = ws.tsh; g.Al = ws.tsl; g.lda = kTimeDim;
-        g.Wh = H(h->w.wmod_h); g.Wl = H(h->w.wmod_l); g.ldw = kTimeDim;
-        g.M = (int)pad128(B); g.N = (int)d.n_mod; g.K = kTimeDim;
-        g.bias = h->w.bmod; g.out = ws.mod; g.ldo = (int)d.n_mod;
-        PDK_TRY("gemm(mod)", launch_gemm(EPI_STORE, g, st));
-    }
-    PDK_TRY("precond", launch_precond(x_hat, ws.coef, h->a, h->w.wx, h->w.bx, ws.ba, (int)B, (int)h->Na, (int)Sa, ca, st));
+    PDK_TRY("precond", launch_precond(x_hat, coef, coef_stride, h->a, h->w.wx, h->w.bx, ws.ba, (int)B, (int)h->Na, (int)Sa, ca, st));
 
     // atom encoder (transformers.py:252)
     const size_t plane_a = (size_t)Ha * Sa * Sa, plane_t = (size_t)Hs * St * St;
     for (int l = 0; l < nA; ++l) {
-        int rc = run_block(*h, h->blocks[l], ws, ws.ba, B, Sa, ca, (int)d.hidden_a, h->bias_atom + l * plane_a, st);
+        int rc = run_block(*h, h->blocks[l], ws, mod, mod_stride, ws.ba, B, Sa, ca, (int)d.hidden_a, h->bias_atom + l * plane_a, st);
         if (rc) return rc;
     }
     // downscale (transformers.py:205-212)
@@ -312,7 +318,7 @@ int pdk_dit_denoise(pdk_dit* h, const float* x_hat, const float* t_hat, int64_t 
     PDK_TRY("segment_mean", launch_segment_mean(ws.down, h->tok_start, h->s, ws.bs, (int)B, (int)h->Nt, (int)Sa, (int)St, cs, st));
     // token DiT (transformers.py:255)
     for (int l = 0; l < nT; ++l) {
-        int rc = run_block(*h, h->blocks[nA + l], ws, ws.bs, B, St, cs, (int)d.hidden_s, h->bias_tok + l * plane_t, st);
+        int rc = run_block(*h, h->blocks[nA + l], ws, mod, mod_stride, ws.bs, B, St, cs, (int)d.hidden_s, h->bias_tok + l * plane_t, st);
         if (rc) return rc;
     }
     // upscale (transformers.py:214-216)
@@ -328,14 +334,67 @@ int pdk_dit_denoise(pdk_dit* h, const float* x_hat, const float* t_hat, int64_t 
     PDK_TRY("gather_add", launch_gather_add(ws.ba, ws.up, h->atom2tok, (int)B, (int)h->Na, (int)Sa, (int)St, ca, st));
     // atom decoder (transformers.py:259)
     for (int l = 0; l < nA; ++l) {
-        int rc = run_block(*h, h->blocks[nA + nT + l], ws, ws.ba, B, Sa, ca, (int)d.hidden_a,
+        int rc = run_block(*h, h->blocks[nA + nT + l], ws, mod, mod_stride, ws.ba, B, Sa, ca, (int)d.hidden_a,
                            h->bias_atom + (size_t)(nA + l) * plane_a, st);
         if (rc) return rc;
     }
-    // denoise (transformers.py:228-233)
-    PDK_TRY("denoise_out", launch_denoise_out(ws.ba, x_hat, ws.coef, h->w.norm_r_w, h->w.norm_r_b, h->w.wr, x_denoised,
-                                              (int)B, (int)h->Na, (int)Sa, ca, (float)d.eps, st));
+    // denoise (transformers.py:228-233) [+ the physics-free Euler update, model.py:263-264,278-281]
+    PDK_TRY("denoise_out", launch_denoise_out(ws.ba, x_hat, coef, coef_stride, h->w.norm_r_w, h->w.norm_r_b, h->w.wr, x_denoised,
+                                              (int)B, (int)h->Na, (int)Sa, ca, (float)d.eps, x_next, st));
     return 0;
+}
+
+int pdk_dit_denoise(pdk_dit* h, const float* x_hat, const float* t_hat, int64_t B, void* workspace,
+                    size_t workspace_bytes, float* x_denoised, void* stream) {
+    if (!h || !h->prepared) return fail_msg("pdk_dit_denoise", "no prepared complex");
+    if (!x_hat || !t_hat || !workspace || !x_denoised || B <= 0) return fail_msg("pdk_dit_denoise", "bad argument");
+    Workspace ws = carve(*h, B, h->Sa, h->St, reinterpret_cast<uint8_t*>(workspace));
+    if (ws.bytes > workspace_bytes) return fail_msg("pdk_dit_denoise", "workspace too small");
+    // per-sample noise levels: conditioning rows computed here (2 launches), mod [pad128(B), n_mod], coef [B, kCoefWidth]
+    cudaStream_t st = S(stream);
+    const pdk_dit_dims& d = h->d;
+    PDK_TRY("time_embed", launch_time_embed(t_hat, h->w.freq, h->w.te_w1, h->w.te_b1, h->w.te_w2, h->w.te_b2, (float)d.sigma_data,
+                                            nullptr, ws.tsh, ws.tsl, (int)pad128(B), ws.coef, kCoefWidth, (int)B, st));
+    {
+        GemmArgs g{};
+        g.Ah = ws.tsh; g.Al = ws.tsl; g.lda = kTimeDim;
+        g.Wh = H(h->w.wmod_h); g.Wl = H(h->w.wmod_l); g.ldw = kTimeDim;
+        g.M = (int)pad128(B); g.N = (int)d.n_mod; g.K = kTimeDim;
+        g.bias = h->w.bmod; g.out = ws.mod; g.ldo = (int)d.n_mod;
+        PDK_TRY("gemm(mod)", launch_gemm(EPI_STORE, g, st));
+    }
+    return run_denoise(h, x_hat, ws.mod, (int)d.n_mod, ws.coef, kCoefWidth, B, ws, x_denoised, nullptr, st);
+}
+
+int64_t pdk_dit_cond_width(const pdk_dit* h) { return h ? h->d.n_mod + kCoefWidth : 0; }
+
+int pdk_dit_conditioning_workspace_bytes(const pdk_dit* h, int64_t n, size_t* bytes) {
+    if (!h || !bytes || n <= 0) return fail_msg("pdk_dit_conditioning_workspace_bytes", "bad argument");
+    *bytes = 2 * align_up((size_t)pad128(n) * kTimeDim * 2);
+    return 0;
+}
+
+int pdk_dit_conditioning(pdk_dit* h, const float* t_hat, int64_t n, void* workspace, size_t workspace_bytes, float* table,
+                         int64_t table_ld, void* stream) {
+    if (!h || !h->have_weights) return fail_msg("pdk_dit_conditioning", "weights not set");
+    if (!t_hat || !workspace || !table || n <= 0) return fail_msg("pdk_dit_conditioning", "bad argument");
+    if (table_ld < h->d.n_mod + kCoefWidth || table_ld % 4) return fail_msg("pdk_dit_conditioning", "table_ld < n_mod + 8 or not a multiple of 4");
+    const size_t plane = align_up((size_t)pad128(n) * kTimeDim * 2);
+    if (2 * plane > workspace_bytes) return fail_msg("pdk_dit_conditioning", "workspace too small");
+    uint8_t* base = reinterpret_cast<uint8_t*>(workspace);
+    return run_conditioning(h, t_hat, n, reinterpret_cast<__half*>(base), reinterpret_cast<__half*>(base + plane), table, table_ld,
+                            S(stream));
+}
+
+int pdk_dit_denoise_cond(pdk_dit* h, const float* x_hat, const float* cond, int64_t cond_stride, int64_t B, void* workspace,
+                         size_t workspace_bytes, float* x_denoised, float* x_next, void* stream) {
+    if (!h || !h->prepared) return fail_msg("pdk_dit_denoise_cond", "no prepared complex");
+    if (!x_hat || !cond || !workspace || !x_denoised || B <= 0) return fail_msg("pdk_dit_denoise_cond", "bad argument");
+    if (cond_stride != 0 && (cond_stride < h->d.n_mod + kCoefWidth || cond_stride % 4))
+        return fail_msg("pdk_dit_denoise_cond", "cond_stride must be 0 (shared row) or >= n_mod + 8 and a multiple of 4");
+    Workspace ws = carve(*h, B, h->Sa, h->St, reinterpret_cast<uint8_t*>(workspace));
+    if (ws.bytes > workspace_bytes) return fail_msg("pdk_dit_denoise_cond", "workspace too small");
+    return run_denoise(h, x_hat, cond, (int)cond_stride, cond + h->d.n_mod, (int)cond_stride, B, ws, x_denoised, x_next, S(stream));
 }
 
 // ---------------------------------------------------------------------------------- sampler ops
@@ -415,7 +474,7 @@ int pdk_op_pair_bias(const float* pair, const float* mask, const float* wfoldT, 
 }
 int pdk_op_time_embed(const float* t_hat, const float* freq, const float* w1, const float* b1, const float* w2,
                       const float* b2, float sigma_data, float* tsilu, float* coef, int64_t B, void* stream) {
-    PDK_TRY("time_embed", launch_time_embed(t_hat, freq, w1, b1, w2, b2, sigma_data, tsilu, nullptr, nullptr, 0, coef, (int)B, S(stream)));
+    PDK_TRY("time_embed", launch_time_embed(t_hat, freq, w1, b1, w2, b2, sigma_data, tsilu, nullptr, nullptr, 0, coef, 4, (int)B, S(stream)));
     return 0;
 }
 int pdk_op_mod_gemv(const float* tsilu, const float* wmod, const float* bmod, float* mod, int64_t B, int64_t n_mod,
@@ -493,7 +552,7 @@ int pdk_op_attention(const void* q, const void* k, const void* v, const float* b
 }
 int pdk_op_precond(const float* x_hat, const float* coef, const float* a, const float* wx, const float* bx, float* ba,
                    int64_t B, int64_t Na, int64_t S_pad, int64_t c_a, void* stream) {
-    PDK_TRY("precond", launch_precond(x_hat, coef, a, wx, bx, ba, (int)B, (int)Na, (int)S_pad, (int)c_a, S(stream)));
+    PDK_TRY("precond", launch_precond(x_hat, coef, 4, a, wx, bx, ba, (int)B, (int)Na, (int)S_pad, (int)c_a, S(stream)));
     return 0;
 }
 int pdk_op_segment_mean(const float* h, const int32_t* tok_start, const float* s, float* bs, int64_t B, int64_t Nt,
@@ -509,7 +568,7 @@ int pdk_op_gather_add(float* ba, const float* up, const int32_t* atom2tok, int64
 int pdk_op_denoise_out(const float* ba, const float* x_hat, const float* coef, const float* ln_w, const float* ln_b,
                        const float* wr, float* x_den, int64_t B, int64_t Na, int64_t S_pad, int64_t c_a, float eps,
                        void* stream) {
-    PDK_TRY("denoise_out", launch_denoise_out(ba, x_hat, coef, ln_w, ln_b, wr, x_den, (int)B, (int)Na, (int)S_pad, (int)c_a, eps, S(stream)));
+    PDK_TRY("denoise_out", launch_denoise_out(ba, x_hat, coef, 4, ln_w, ln_b, wr, x_den, (int)B, (int)Na, (int)S_pad, (int)c_a, eps, nullptr, S(stream)));
     return 0;
 }
 

@@ -22,31 +22,53 @@ constexpr int   kTimeDim = 256;          // timestep_embeddings.py:157
 PDK_DEV void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 PDK_DEV void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// Measurement switches (A/B toggles read from the environment) exist ONLY in debug builds compiled with -DPDK_MEASURE
+// (tools/gemm_variants.sh); in the release library they are compile-time false, so no environment variable can change
+// the hot path.
+#ifdef PDK_MEASURE
+inline bool measure_switch(const char* name) { return getenv(name) != nullptr; }
+#else
+constexpr bool measure_switch(const char*) { return false; }
+#endif
+
+// Per-device one-time setup (cudaFuncSetAttribute, SM count): keyed by the current device so that a process driving
+// several GPUs configures each of them.
+constexpr int kMaxDevices = 64;
+struct PerDevice {
+    bool done[kMaxDevices] = {};
+    int sms[kMaxDevices] = {};
+};
+inline cudaError_t current_device(int* dev) {
+    cudaError_t e = cudaGetDevice(dev);
+    if (e != cudaSuccess) return e;
+    return (*dev < 0 || *dev >= kMaxDevices) ? cudaErrorInvalidDevice : cudaSuccess;
+}
+inline cudaError_t device_sm_count(int* sms) {
+    static PerDevice pd;
+    int dev = 0;
+    cudaError_t e = current_device(&dev);
+    if (e != cudaSuccess) return e;
+    if (!pd.done[dev]) {
+        if ((e = cudaDeviceGetAttribute(&pd.sms[dev], cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+        pd.done[dev] = true;
+    }
+    *sms = pd.sms[dev];
+    return cudaSuccess;
+}
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device); `pd` is the kernel's own static PerDevice
+template <typename K>
+inline cudaError_t ensure_smem(PerDevice& pd, K kernel, int bytes) {
+    int dev = 0;
+    cudaError_t e = current_device(&dev);
+    if (e != cudaSuccess) return e;
+    if (!pd.done[dev]) {
+        if ((e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
+        pd.done[dev] = true;
+    }
+    return cudaSuccess;
+}
+
 PDK_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-// ---- async copies --------------------------------------------------------------------------
-PDK_DEV void cp_async16(uint32_t dst, const void* src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src));
-}
-PDK_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N> PDK_DEV void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
-
-// ---- warp-level matrix fragments (legacy tensor path; see DESIGN.md "v1 kernels") -----------
-PDK_DEV void ldmatrix_x4(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, uint32_t addr) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
-                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
-}
-PDK_DEV void ldmatrix_x4_trans(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, uint32_t addr) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
-                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
-}
-// D(16x8,f32) += A(16x16,f16,row) * B(16x8,f16,col)
-PDK_DEV void mma_f16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm volatile(
-        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
-        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
 
 // ---- split-fp16 number format ----------------------------------------------------------------
 // x (fp32) ~= hi + lo with hi = fp16(x), lo = fp16(x - hi): 22 significant bits.  A product a*b is
@@ -65,19 +87,6 @@ PDK_DEV float inv_sqrt(float x) {
     const float y = rsqrtf(x);
     return y * fmaf(-0.5f * x * y, y, 1.5f);
 }
-// same, for values known to lie in [0, 1] (softmax probabilities)
-PDK_DEV void split2_unit(float x0, float x1, uint32_t& hi, uint32_t& lo) {
-    __half2 h = __floats2half2_rn(x0, x1);
-    float2 hf = __half22float2(h);
-    __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
-    hi = *reinterpret_cast<uint32_t*>(&h);
-    lo = *reinterpret_cast<uint32_t*>(&l);
-}
-
-// 64-byte-row tile (32 halves per row): 16-byte chunk c of row r lives at chunk c ^ ((r>>1)&3).
-// Makes both the cp.async fills and every 8-row ldmatrix phase bank-conflict free.
-PDK_DEV uint32_t swz64(int row, int chunk) { return (uint32_t)(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4)); }
-
 // ---- math --------------------------------------------------------------------------------------
 PDK_DEV float ex2(float x) {
     float y;
@@ -136,7 +145,7 @@ template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    static const int pdl = getenv("PDK_NO_PDL") == nullptr;     // measurement switch; PDL is on in production
+    static const int pdl = !measure_switch("PDK_NO_PDL");
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = pdl;

@@ -20,53 +20,60 @@ __device__ __forceinline__ float block_sum(float v, float* scratch) {
     for (int i = 0; i < nw; ++i) r += scratch[i];
     return r;
 }
-__device__ __forceinline__ double block_sum(double v, double* scratch) {
-    v = warp_sum(v);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-    __syncthreads();
-    if (lane == 0) scratch[warp] = v;
-    __syncthreads();
-    double r = 0.0;
-    for (int i = 0; i < nw; ++i) r += scratch[i];
-    return r;
-}
-
-// _uniform_sphere_point (tensor_utils.py:545-562): phi = u*2*pi, theta = acos(u*2-1); trig evaluated in
-// fp64 and rounded once (correctly rounded fp32 results, see glue.cu note).
-__device__ __forceinline__ void sphere_point(float u_phi, float u_theta, float (&p)[3]) {
-    const float phi = __fmul_rn(__fmul_rn(u_phi, 2.0f), 3.14159265358979323846f);
+// One component of _uniform_sphere_point (tensor_utils.py:545-562): phi = u*2*pi, theta = acos(u*2-1); trig evaluated in
+// fp64 and rounded once (correctly rounded fp32 results, see glue.cu note).  which: 0 cos(phi), 1 sin(phi), 2 cos(theta),
+// 3 sin(theta).  The eight values a rotation needs are evaluated by eight different warps at the same time: a single
+// thread doing all ten fp64 transcendentals in sequence was most of the old kernel's 16 us.
+__device__ __forceinline__ float sphere_trig(float u_phi, float u_theta, int which) {
+    if (which < 2) {
+        const float phi = __fmul_rn(__fmul_rn(u_phi, 2.0f), 3.14159265358979323846f);
+        return which == 0 ? (float)cos((double)phi) : (float)sin((double)phi);
+    }
     const float theta = (float)acos((double)__fsub_rn(__fmul_rn(u_theta, 2.0f), 1.0f));
-    const float cp = (float)cos((double)phi), sp = (float)sin((double)phi);
-    const float ct = (float)cos((double)theta), stt = (float)sin((double)theta);
-    p[0] = __fmul_rn(cp, stt);
-    p[1] = __fmul_rn(sp, stt);
-    p[2] = ct;
+    return which == 2 ? (float)cos((double)theta) : (float)sin((double)theta);
 }
 
-// centre_random_augmentation (tensor_utils.py:576-586) fused with diffuse (model.py:70-85).  CTA per sample.
-__global__ void __launch_bounds__(256) centre_augment_kernel(const float* __restrict__ x, const float* __restrict__ x_exists,
+constexpr int COORD_THREADS = 256, COORD_WARPS = COORD_THREADS / 32;
+constexpr int COORD_CHUNK = 256;         // atoms transformed per CTA
+
+// centre_random_augmentation (tensor_utils.py:576-586) fused with diffuse (model.py:70-85).
+// Grid (atom chunks, samples): every CTA of a sample recomputes the sample's masked mean and rotation (24 KB of
+// L2-resident reads and the same arithmetic in the same order, hence bit-identical across CTAs) and transforms its own
+// chunk of 256 atoms, so a 2048-atom sample runs on 8 SMs instead of 1.
+__global__ void __launch_bounds__(COORD_THREADS) centre_augment_kernel(const float* __restrict__ x, const float* __restrict__ x_exists,
                                                              const float* __restrict__ u4, const float* __restrict__ trans,
                                                              const float* __restrict__ noise, float lambda,
                                                              float noise_scale, float trans_scale,
                                                              float* __restrict__ x_out, int Na) {
     griddep_launch();
     griddep_wait();
-    __shared__ float scratch[8];
+    __shared__ float part[COORD_WARPS][4];
+    __shared__ float sTrig[8];
     __shared__ float sR[9];
     __shared__ float sMean[3];
-    const int b = blockIdx.x, tid = threadIdx.x;
+    const int b = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const float* xb = x + (size_t)b * Na * 3;
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, sm = 0.f;
-    for (int i = tid; i < Na; i += blockDim.x) {
+    for (int i = tid; i < Na; i += COORD_THREADS) {
         const float m = x_exists[i];
         s0 += xb[3 * i] * m; s1 += xb[3 * i + 1] * m; s2 += xb[3 * i + 2] * m; sm += m;
     }
-    s0 = block_sum(s0, scratch); s1 = block_sum(s1, scratch); s2 = block_sum(s2, scratch); sm = block_sum(sm, scratch);
+    s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2); sm = warp_sum(sm);
+    if (lane == 0) {
+        part[warp][0] = s0; part[warp][1] = s1; part[warp][2] = s2; part[warp][3] = sm;
+        // warp w evaluates trig value w: (cos phi0, sin phi0, cos theta0, sin theta0, cos phi1, sin phi1, cos theta1, sin theta1)
+        const int pt = warp >> 2;
+        sTrig[warp] = sphere_trig(u4[4 * b + 2 * pt], u4[4 * b + 2 * pt + 1], warp & 3);
+    }
+    __syncthreads();
     if (tid == 0) {
-        sMean[0] = s0 / sm; sMean[1] = s1 / sm; sMean[2] = s2 / sm;
+        float t[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int w = 0; w < COORD_WARPS; ++w)
+            for (int k = 0; k < 4; ++k) t[k] += part[w][k];
+        sMean[0] = t[0] / t[3]; sMean[1] = t[1] / t[3]; sMean[2] = t[2] / t[3];
         float e0[3], u1[3], e1[3];
-        sphere_point(u4[4 * b + 0], u4[4 * b + 1], e0);
-        sphere_point(u4[4 * b + 2], u4[4 * b + 3], u1);
+        e0[0] = __fmul_rn(sTrig[0], sTrig[3]); e0[1] = __fmul_rn(sTrig[1], sTrig[3]); e0[2] = sTrig[2];
+        u1[0] = __fmul_rn(sTrig[4], sTrig[7]); u1[1] = __fmul_rn(sTrig[5], sTrig[7]); u1[2] = sTrig[6];
         // uniform_random_rotation (tensor_utils.py:565-573): Gram-Schmidt + cross product, rows e0,e1,e2
         const float dot = __fadd_rn(__fadd_rn(__fmul_rn(u1[0], e0[0]), __fmul_rn(u1[1], e0[1])), __fmul_rn(u1[2], e0[2]));
         for (int k = 0; k < 3; ++k) e1[k] = __fsub_rn(u1[k], __fmul_rn(e0[k], dot));
@@ -81,7 +88,8 @@ __global__ void __launch_bounds__(256) centre_augment_kernel(const float* __rest
     __syncthreads();
     const float t0 = __fmul_rn(trans_scale, trans[3 * b]), t1 = __fmul_rn(trans_scale, trans[3 * b + 1]),
                 t2 = __fmul_rn(trans_scale, trans[3 * b + 2]);
-    for (int i = tid; i < Na; i += blockDim.x) {
+    const int i_end = min(Na, (int)(blockIdx.x + 1) * COORD_CHUNK);
+    for (int i = blockIdx.x * COORD_CHUNK + tid; i < i_end; i += COORD_THREADS) {
         const float a0 = __fsub_rn(xb[3 * i], sMean[0]), a1 = __fsub_rn(xb[3 * i + 1], sMean[1]),
                     a2 = __fsub_rn(xb[3 * i + 2], sMean[2]);
         float o[3];
@@ -241,20 +249,41 @@ __device__ void kabsch3(const double H[3][3], double Q[3][3]) {
         for (int j = 0; j < 3; ++j) Q[i][j] = v1[i] * u1[j] + v2[i] * u2[j] + v3[i] * u3[j];   // Q = V U^T
 }
 
+// Sums K per-thread fp64 values over the CTA with ONE barrier pair (the old code called block_sum once per value:
+// 16 x 2 barriers per launch); every thread returns with all K totals, summed in a fixed order.
+template <int K>
+__device__ __forceinline__ void block_sum_n(double (&v)[K], double (*part)[16]) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int k = 0; k < K; ++k) v[k] = warp_sum(v[k]);
+    __syncthreads();                  // `part` may still be read from the previous call
+    if (lane == 0)
+#pragma unroll
+        for (int k = 0; k < K; ++k) part[warp][k] = v[k];
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        double r = 0.0;
+        for (int w = 0; w < COORD_WARPS; ++w) r += part[w][k];
+        v[k] = r;
+    }
+}
+
 // weighted_rigid_align (tensor_utils.py:724-778): returns x_gt rotated + translated onto x_pred's frame.
-// x_pred = x_den * x_exists is formed on the fly (model.py:245).  CTA per sample.
-__global__ void __launch_bounds__(256) rigid_align_kernel(const float* __restrict__ x_den, const float* __restrict__ x_exists,
+// x_pred = x_den * x_exists is formed on the fly (model.py:245).  Grid (atom chunks, samples): like centre_augment every
+// CTA of a sample recomputes the (tiny, ligand-only) moments and the 3x3 Kabsch and transforms its own 256 atoms.
+__global__ void __launch_bounds__(COORD_THREADS) rigid_align_kernel(const float* __restrict__ x_den, const float* __restrict__ x_exists,
                                                           const float* __restrict__ x_gt, int gt_batched,
                                                           const float* __restrict__ w, float* __restrict__ aligned, int Na) {
     griddep_launch();
     griddep_wait();
-    __shared__ double scratch[8];
+    __shared__ double part[COORD_WARPS][16];
     __shared__ float sQ[9], sMuP[3], sMuG[3];
-    const int b = blockIdx.x, tid = threadIdx.x;
+    const int b = blockIdx.y, tid = threadIdx.x;
     const float* xp = x_den + (size_t)b * Na * 3;
     const float* xg = x_gt + (gt_batched ? (size_t)b * Na * 3 : 0);
     double acc[7] = {0, 0, 0, 0, 0, 0, 0};
-    for (int i = tid; i < Na; i += blockDim.x) {
+    for (int i = tid; i < Na; i += COORD_THREADS) {
         const float wi = w[i];
         if (wi != 0.f) {
             const float m = x_exists[i];
@@ -262,22 +291,21 @@ __global__ void __launch_bounds__(256) rigid_align_kernel(const float* __restric
             for (int k = 0; k < 3; ++k) { acc[1 + k] += (double)wi * (xp[3 * i + k] * m); acc[4 + k] += (double)wi * xg[3 * i + k]; }
         }
     }
-    for (int k = 0; k < 7; ++k) acc[k] = block_sum(acc[k], scratch);
-    if (tid == 0)
-        for (int k = 0; k < 3; ++k) { sMuP[k] = (float)(acc[1 + k] / acc[0]); sMuG[k] = (float)(acc[4 + k] / acc[0]); }
-    __syncthreads();
+    block_sum_n<7>(acc, part);
+    const float muP[3] = {(float)(acc[1] / acc[0]), (float)(acc[2] / acc[0]), (float)(acc[3] / acc[0])};
+    const float muG[3] = {(float)(acc[4] / acc[0]), (float)(acc[5] / acc[0]), (float)(acc[6] / acc[0])};
     double h[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    for (int i = tid; i < Na; i += blockDim.x) {
+    for (int i = tid; i < Na; i += COORD_THREADS) {
         const float wi = w[i];
         if (wi != 0.f) {
             const float m = x_exists[i];
             float gp[3], pp[3];
-            for (int k = 0; k < 3; ++k) { gp[k] = xg[3 * i + k] - sMuG[k]; pp[k] = xp[3 * i + k] * m - sMuP[k]; }
+            for (int k = 0; k < 3; ++k) { gp[k] = xg[3 * i + k] - muG[k]; pp[k] = xp[3 * i + k] * m - muP[k]; }
             for (int j = 0; j < 3; ++j)
                 for (int k = 0; k < 3; ++k) h[3 * j + k] += (double)wi * gp[j] * pp[k];
         }
     }
-    for (int k = 0; k < 9; ++k) h[k] = block_sum(h[k], scratch);
+    block_sum_n<9>(h, part);
     if (tid == 0) {
         double H[3][3], Q[3][3];
         for (int j = 0; j < 3; ++j)
@@ -285,9 +313,11 @@ __global__ void __launch_bounds__(256) rigid_align_kernel(const float* __restric
         kabsch3(H, Q);
         for (int j = 0; j < 3; ++j)
             for (int k = 0; k < 3; ++k) sQ[3 * j + k] = (float)Q[j][k];
+        for (int k = 0; k < 3; ++k) { sMuP[k] = muP[k]; sMuG[k] = muG[k]; }
     }
     __syncthreads();
-    for (int i = tid; i < Na; i += blockDim.x) {
+    const int i_end = min(Na, (int)(blockIdx.x + 1) * COORD_CHUNK);
+    for (int i = blockIdx.x * COORD_CHUNK + tid; i < i_end; i += COORD_THREADS) {
         const float g0 = xg[3 * i] - sMuG[0], g1 = xg[3 * i + 1] - sMuG[1], g2 = xg[3 * i + 2] - sMuG[2];
         float* dst = aligned + ((size_t)b * Na + i) * 3;
 #pragma unroll
@@ -307,7 +337,7 @@ cudaError_t launch_centre_augment(const float* x, const float* x_exists, const f
                                   const float* noise, float lambda, float noise_scale, float trans_scale,
                                   float* x_out, int B, int Na, cudaStream_t st) {
     if (B <= 0 || Na <= 0) return cudaErrorInvalidValue;
-    PDK_LAUNCH_CHECK(launch_pdl(centre_augment_kernel, dim3(B), dim3(256), (size_t)(0), st, x, x_exists, u4, trans, noise, lambda, noise_scale, trans_scale, x_out, Na));
+    PDK_LAUNCH_CHECK(launch_pdl(centre_augment_kernel, dim3((Na + COORD_CHUNK - 1) / COORD_CHUNK, B), dim3(COORD_THREADS), (size_t)(0), st, x, x_exists, u4, trans, noise, lambda, noise_scale, trans_scale, x_out, Na));
     return cudaGetLastError();
 }
 
@@ -336,7 +366,7 @@ cudaError_t launch_template_pick(const float* eps, const float* ref_poses, const
 cudaError_t launch_rigid_align(const float* x_den, const float* x_exists, const float* x_gt, int gt_batched,
                                const float* w, float* aligned, int B, int Na, cudaStream_t st) {
     if (B <= 0 || Na <= 0) return cudaErrorInvalidValue;
-    PDK_LAUNCH_CHECK(launch_pdl(rigid_align_kernel, dim3(B), dim3(256), (size_t)(0), st, x_den, x_exists, x_gt, gt_batched, w, aligned, Na));
+    PDK_LAUNCH_CHECK(launch_pdl(rigid_align_kernel, dim3((Na + COORD_CHUNK - 1) / COORD_CHUNK, B), dim3(COORD_THREADS), (size_t)(0), st, x_den, x_exists, x_gt, gt_batched, w, aligned, Na));
     return cudaGetLastError();
 }
 

@@ -416,14 +416,10 @@ template <int EPI, bool PAIR, bool WIDE>
 cudaError_t launch_variant(const GemmArgs& a, cudaStream_t st, int num_sms) {
     constexpr int SMEM_BYTES = smem_bytes<PAIR, WIDE>();
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory");
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_umma_kernel<EPI, PAIR, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
-    CUtensorMap mAh, mAl, mWh, mWl;
+    static PerDevice configured;
     cudaError_t e;
+    if ((e = ensure_smem(configured, gemm_umma_kernel<EPI, PAIR, WIDE>, SMEM_BYTES)) != cudaSuccess) return e;
+    CUtensorMap mAh, mAl, mWh, mWl;
     constexpr int W_ROWS = PAIR ? BN / 2 : BN;
     if ((e = get_tensor_map_f16(a.Ah, a.M, a.K, a.lda, BM, BK, 128, &mAh)) != cudaSuccess) return e;
     if ((e = get_tensor_map_f16(a.Al, a.M, a.K, a.lda, BM, BK, 128, &mAl)) != cudaSuccess) return e;
@@ -436,7 +432,7 @@ cudaError_t launch_variant(const GemmArgs& a, cudaStream_t st, int num_sms) {
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = st;
     cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = getenv("PDK_NO_PDL") == nullptr;
+    attr[0].val.programmaticStreamSerializationAllowed = !measure_switch("PDK_NO_PDL");
     attr[1].id = cudaLaunchAttributeClusterDimension;
     attr[1].val.clusterDim.x = 2; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = PAIR ? 2 : 1;
@@ -446,22 +442,19 @@ cudaError_t launch_variant(const GemmArgs& a, cudaStream_t st, int num_sms) {
 
 template <int EPI>
 cudaError_t launch_one(const GemmArgs& a, cudaStream_t st) {
-    static int num_sms = 0;
-    if (num_sms == 0) {
-        int dev = 0;
-        cudaError_t e;
-        if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
-        if ((e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
-    }
-    static const bool allow_pair = getenv("PDK_NO_PAIR") == nullptr;       // measurement switch
-    static const bool force_pair = getenv("PDK_FORCE_PAIR") != nullptr;    // measurement switch
+    int num_sms = 0;
+    cudaError_t e;
+    if ((e = device_sm_count(&num_sms)) != cudaSuccess) return e;
+    // measurement switches: compile-time false in the release build (common.cuh)
+    static const bool allow_pair = !measure_switch("PDK_NO_PAIR");
+    static const bool force_pair = measure_switch("PDK_FORCE_PAIR");
     const bool big = (long long)a.K * a.N >= 700000;       // see the header: small-K shapes lose on the pair tiling
-    static const bool allow_wide = getenv("PDK_NO_WIDE") == nullptr;       // measurement switch
+    static const bool allow_wide = !measure_switch("PDK_NO_WIDE");
     const bool pair = allow_pair && a.M % (2 * BM) == 0 && (big || force_pair);
     if constexpr (EPI == EPI_SWIGLU) {        // 32-byte rows per plane either way: always the narrow staging
         return pair ? launch_variant<EPI, true, false>(a, st, num_sms) : launch_variant<EPI, false, false>(a, st, num_sms);
     } else {
-        static const bool wide_all = getenv("PDK_WIDE_ALL") != nullptr;      // measurement switch
+        static const bool wide_all = measure_switch("PDK_WIDE_ALL");
         const bool wide = allow_wide && (pair || a.K <= 2 * BK || wide_all);
         if (pair) return wide ? launch_variant<EPI, true, true>(a, st, num_sms) : launch_variant<EPI, true, false>(a, st, num_sms);
         return wide ? launch_variant<EPI, false, true>(a, st, num_sms) : launch_variant<EPI, false, false>(a, st, num_sms);

@@ -21,7 +21,7 @@ __global__ void __launch_bounds__(256) time_embed_kernel(const float* __restrict
                                                          const float* __restrict__ w2, const float* __restrict__ b2,
                                                          float sigma_data, float* __restrict__ tsilu,
                                                          __half* __restrict__ ts_h, __half* __restrict__ ts_l,
-                                                         float* __restrict__ coef, int B) {
+                                                         float* __restrict__ coef, int coef_ld, int B) {
     griddep_launch();
     griddep_wait();
     __shared__ __align__(16) float proj[kTimeDim];
@@ -35,10 +35,11 @@ __global__ void __launch_bounds__(256) time_embed_kernel(const float* __restrict
     const float sd2 = sigma_data * sigma_data;
     const float t2 = t * t;
     if (tid == 0) {
-        coef[4 * b + 0] = 1.0f / sqrtf(t2 + sd2);                      // c_in   (:219)
-        coef[4 * b + 1] = sd2 / (sd2 + t2);                            // c_skip (:229)
-        coef[4 * b + 2] = sigma_data * t / sqrtf(sd2 + t2);            // c_out  (:230)
-        coef[4 * b + 3] = t;
+        float* cf = coef + (size_t)coef_ld * b;
+        cf[0] = 1.0f / sqrtf(t2 + sd2);                      // c_in   (:219)
+        cf[1] = sd2 / (sd2 + t2);                            // c_skip (:229)
+        cf[2] = sigma_data * t / sqrtf(sd2 + t2);            // c_out  (:230)
+        cf[3] = t;
     }
     const float c_noise = (float)log((double)(t / sigma_data)) / 4.0f;  // (:220)
     const float t_in = t * c_noise;                                     // (:223) sic
@@ -177,7 +178,7 @@ __global__ void __launch_bounds__(256) split_kernel(const float* __restrict__ x,
 __global__ void __launch_bounds__(256) precond_kernel(const float* __restrict__ x_hat, const float* __restrict__ coef,
                                                       const float* __restrict__ a, const float* __restrict__ wx,
                                                       const float* __restrict__ bx, float* __restrict__ ba, int B,
-                                                      int Na, int S_pad, int c_a) {
+                                                      int Na, int S_pad, int c_a, int coef_stride) {
     griddep_launch();
     griddep_wait();
     const int per_row = c_a / 4;
@@ -188,7 +189,7 @@ __global__ void __launch_bounds__(256) precond_kernel(const float* __restrict__ 
         const int s = (int)(r % (uint32_t)S_pad), b = (int)(r / (uint32_t)S_pad);
         float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
         if (s < Na) {
-            const float c_in = coef[4 * b];
+            const float c_in = coef[coef_stride * b];
             const float* xp = x_hat + ((size_t)b * Na + s) * 3;
             const float x0 = xp[0] * c_in, x1 = xp[1] * c_in, x2 = xp[2] * c_in;
             const float4 av = *reinterpret_cast<const float4*>(a + (size_t)s * c_a + 4 * c4);
@@ -262,7 +263,7 @@ __global__ void __launch_bounds__(256) denoise_out_kernel(const float* __restric
                                                           const float* __restrict__ coef, const float* __restrict__ ln_w,
                                                           const float* __restrict__ ln_b, const float* __restrict__ wr,
                                                           float* __restrict__ x_den, int B, int Na, int S_pad,
-                                                          float eps) {
+                                                          float eps, int coef_stride, float* __restrict__ x_next) {
     griddep_launch();
     griddep_wait();
     const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -284,10 +285,18 @@ __global__ void __launch_bounds__(256) denoise_out_kernel(const float* __restric
         out[j] = warp_sum(fmaf(y3, w.w, fmaf(y2, w.z, fmaf(y1, w.y, y0 * w.x))));
     }
     if (lane < 3) {
-        const float c_skip = coef[4 * b + 1], c_out = coef[4 * b + 2];
+        const float* cf = coef + (size_t)coef_stride * b;
+        const float c_skip = cf[1], c_out = cf[2];
         const float r_j = lane == 0 ? out[0] : (lane == 1 ? out[1] : out[2]);
         const size_t o = ((size_t)b * Na + s) * 3 + lane;
-        x_den[o] = __fadd_rn(__fmul_rn(c_skip, x_hat[o]), __fmul_rn(c_out, r_j));
+        const float xh = x_hat[o];
+        const float xd = __fadd_rn(__fmul_rn(c_skip, xh), __fmul_rn(c_out, r_j));
+        x_den[o] = xd;
+        if (x_next != nullptr) {      // fused Euler update without physics (model.py:263-264,278-281), reference operation order
+            const float th = cf[3], t_next = cf[4], eta = cf[5];      // per-step scalars live in the conditioning row
+            const float d = __fsub_rn(xh, xd) / th;
+            x_next[o] = __fadd_rn(xh, __fmul_rn(__fmul_rn(eta, __fsub_rn(t_next, th)), d));
+        }
     }
 }
 
@@ -300,10 +309,10 @@ inline int grid_for(size_t n, int block = 256, int cap = 148 * 16) {
 
 cudaError_t launch_time_embed(const float* t_hat, const float* freq, const float* w1, const float* b1,
                               const float* w2, const float* b2, float sigma_data, float* tsilu, __half* ts_h,
-                              __half* ts_l, int rows_padded, float* coef, int B, cudaStream_t st) {
-    if (B <= 0 || (ts_h != nullptr && rows_padded < B)) return cudaErrorInvalidValue;
+                              __half* ts_l, int rows_padded, float* coef, int coef_ld, int B, cudaStream_t st) {
+    if (B <= 0 || coef_ld < 4 || (ts_h != nullptr && rows_padded < B)) return cudaErrorInvalidValue;
     PDK_LAUNCH_CHECK(launch_pdl(time_embed_kernel, dim3(ts_h != nullptr ? rows_padded : B), dim3(256), (size_t)(0), st, t_hat, freq, w1, b1, w2, b2, sigma_data, tsilu, ts_h,
-                                                                       ts_l, coef, B));
+                                                                       ts_l, coef, coef_ld, B));
     return cudaGetLastError();
 }
 
@@ -333,10 +342,10 @@ cudaError_t launch_split(const float* x, __half* xh, __half* xl, size_t n, cudaS
     return cudaGetLastError();
 }
 
-cudaError_t launch_precond(const float* x_hat, const float* coef, const float* a, const float* wx, const float* bx,
-                           float* ba, int B, int Na, int S_pad, int c_a, cudaStream_t st) {
+cudaError_t launch_precond(const float* x_hat, const float* coef, int coef_stride, const float* a, const float* wx,
+                           const float* bx, float* ba, int B, int Na, int S_pad, int c_a, cudaStream_t st) {
     if (c_a % 4 || Na > S_pad || (size_t)B * S_pad * (c_a / 4) >= (1ull << 31)) return cudaErrorInvalidValue;
-    PDK_LAUNCH_CHECK(launch_pdl(precond_kernel, dim3(grid_for((size_t)B * S_pad * (c_a / 4))), dim3(256), (size_t)(0), st, x_hat, coef, a, wx, bx, ba, B, Na, S_pad, c_a));
+    PDK_LAUNCH_CHECK(launch_pdl(precond_kernel, dim3(grid_for((size_t)B * S_pad * (c_a / 4))), dim3(256), (size_t)(0), st, x_hat, coef, a, wx, bx, ba, B, Na, S_pad, c_a, coef_stride));
     return cudaGetLastError();
 }
 
@@ -355,11 +364,12 @@ cudaError_t launch_gather_add(float* ba, const float* up, const int* atom2tok, i
     return cudaGetLastError();
 }
 
-cudaError_t launch_denoise_out(const float* ba, const float* x_hat, const float* coef, const float* ln_w,
+cudaError_t launch_denoise_out(const float* ba, const float* x_hat, const float* coef, int coef_stride, const float* ln_w,
                                const float* ln_b, const float* wr, float* x_den, int B, int Na, int S_pad,
-                               int c_a, float eps, cudaStream_t st) {
+                               int c_a, float eps, float* x_next, cudaStream_t st) {
     if (c_a != 128) return cudaErrorInvalidValue;
-    PDK_LAUNCH_CHECK(launch_pdl(denoise_out_kernel, dim3((B * Na + 7) / 8), dim3(256), (size_t)(0), st, ba, x_hat, coef, ln_w, ln_b, wr, x_den, B, Na, S_pad, eps));
+    PDK_LAUNCH_CHECK(launch_pdl(denoise_out_kernel, dim3((B * Na + 7) / 8), dim3(256), (size_t)(0), st, ba, x_hat, coef, ln_w, ln_b, wr, x_den, B, Na, S_pad, eps,
+                                coef_stride, x_next));
     return cudaGetLastError();
 }
 

@@ -72,10 +72,14 @@ cudaError_t launch_pair_bias(const float* pair, const float* mask, const float* 
 
 // ----------------------------------------------------------------------------- conditioning / glue
 // t_hat[B] -> SiLU(time_embedder(t_hat * c_noise)) as fp32 tsilu[B,256] (optional) and/or as split planes
-// ts_h/ts_l [rows_padded,256] (rows >= B zeroed: the A operand of the modulation GEMM); coef[B,4] = (c_in, c_skip, c_out, t_hat)
+// ts_h/ts_l [rows_padded,256] (rows >= B zeroed: the A operand of the modulation GEMM); coef rows (leading dimension
+// coef_ld >= 4 floats) receive (c_in, c_skip, c_out, t_hat) in their first four entries.  A conditioning row as the
+// denoiser consumes it is kCoefWidth = 8 floats: (c_in, c_skip, c_out, t_hat, t_next, eta, -, -); t_next / eta are
+// written by the caller of the sampler and only read by the fused Euler update.
+constexpr int kCoefWidth = 8;
 cudaError_t launch_time_embed(const float* t_hat, const float* freq, const float* w1, const float* b1,
                               const float* w2, const float* b2, float sigma_data, float* tsilu, __half* ts_h,
-                              __half* ts_l, int rows_padded, float* coef, int B, cudaStream_t st);
+                              __half* ts_l, int rows_padded, float* coef, int coef_ld, int B, cudaStream_t st);
 // mod[B,Nmod] = tsilu[B,256] * wmod[Nmod,256]^T + bmod   (all AdaLN-Zero linears of the model at once)
 cudaError_t launch_mod_gemv(const float* tsilu, const float* wmod, const float* bmod, float* mod, int B,
                             int Nmod, cudaStream_t st);
@@ -85,18 +89,21 @@ cudaError_t launch_adaln(const float* x, const float* mod, int mod_stride, int m
 // x[rows, c] fp32 -> planes
 cudaError_t launch_split(const float* x, __half* xh, __half* xl, size_t n, cudaStream_t st);
 // ba[B,S_pad,c_a] = W_x (x_hat * c_in) + b_x + a   (rows >= Na zeroed)
-cudaError_t launch_precond(const float* x_hat, const float* coef, const float* a, const float* wx, const float* bx,
-                           float* ba, int B, int Na, int S_pad, int c_a, cudaStream_t st);
+// coef rows are (c_in, c_skip, c_out, t_hat); coef_stride = 4 (one row per sample) or 0 (one row shared by all samples)
+cudaError_t launch_precond(const float* x_hat, const float* coef, int coef_stride, const float* a, const float* wx,
+                           const float* bx, float* ba, int B, int Na, int S_pad, int c_a, cudaStream_t st);
 // bs[B,St_pad,c_s] = segment_sum(h[B,Sa_pad,c_s]) / (n + 1e-3) + s   (rows >= Nt zeroed)
 cudaError_t launch_segment_mean(const float* h, const int* tok_start, const float* s, float* bs, int B, int Nt,
                                 int Sa_pad, int St_pad, int c_s, cudaStream_t st);
 // ba[b, i, :] += up[b, atom2tok[i], :]
 cudaError_t launch_gather_add(float* ba, const float* up, const int* atom2tok, int B, int Na, int Sa_pad,
                               int St_pad, int c_a, cudaStream_t st);
-// x_den = c_skip * x_hat + c_out * W_r LN(ba)
-cudaError_t launch_denoise_out(const float* ba, const float* x_hat, const float* coef, const float* ln_w,
+// x_den = c_skip * x_hat + c_out * W_r LN(ba); x_next != nullptr additionally writes the physics-free Euler update
+// x_next = x_hat + eta * (t_next - t_hat) * (x_hat - x_den) / t_hat   (model.py:263-264,278-281) with t_next, eta taken
+// from entries 4, 5 of the sample's conditioning row
+cudaError_t launch_denoise_out(const float* ba, const float* x_hat, const float* coef, int coef_stride, const float* ln_w,
                                const float* ln_b, const float* wr, float* x_den, int B, int Na, int S_pad,
-                               int c_a, float eps, cudaStream_t st);
+                               int c_a, float eps, float* x_next, cudaStream_t st);
 
 // ----------------------------------------------------------------------------- coordinates / physics
 cudaError_t launch_centre_augment(const float* x, const float* x_exists, const float* u4, const float* trans,

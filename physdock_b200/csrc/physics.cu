@@ -187,13 +187,16 @@ cudaError_t launch_pair_energy_grad(const float* x, const float* exists, const f
     if (B <= 0 || Na <= 0 || n_rows <= 0 || E < 0) return cudaErrorInvalidValue;
     const size_t smem = pair_energy_smem_bytes(Na);
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(pair_energy_grad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static size_t configured[kMaxDevices] = {};      // largest opt-in size set so far, per device
+    int dev = 0;
+    cudaError_t e = current_device(&dev);
+    if (e != cudaSuccess) return e;
+    if (smem > 48 * 1024 && smem > configured[dev]) {
+        e = cudaFuncSetAttribute(pair_energy_grad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(pair_energy_grad_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = smem;
+        configured[dev] = smem;
     }
     // one row per warp until that would be more than ~4 CTAs per SM; then four (amortises the staging of the sample)
     const bool wide = (long long)((n_rows + 7) / 8) * B > 600;

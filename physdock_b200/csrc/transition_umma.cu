@@ -338,18 +338,12 @@ cudaError_t launch_transition_fused(const TransitionArgs& a, cudaStream_t st) {
     if (a.M <= 0 || a.M % TM || a.hidden <= 0 || a.hidden % TK || a.rows_per_sample <= 0 || a.rows_per_sample % TM)
         return cudaErrorInvalidValue;
     if ((a.mod_off % 4) || (a.mod_stride % 4)) return cudaErrorInvalidValue;
-    static bool configured = false;
-    static int num_sms = 0;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(transition_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM);
-        if (e != cudaSuccess) return e;
-        int dev = 0;
-        if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
-        if ((e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
-        configured = true;
-    }
-    CUtensorMap m13h, m13l, m2h, m2l;
+    static PerDevice configured;
+    int num_sms = 0;
     cudaError_t e;
+    if ((e = ensure_smem(configured, transition_umma_kernel, T_SMEM)) != cudaSuccess) return e;
+    if ((e = device_sm_count(&num_sms)) != cudaSuccess) return e;
+    CUtensorMap m13h, m13l, m2h, m2l;
     if ((e = get_tensor_map_f16(a.w13h, 2 * a.hidden, TC, TC, 128, TK, 128, &m13h)) != cudaSuccess) return e;
     if ((e = get_tensor_map_f16(a.w13l, 2 * a.hidden, TC, TC, 128, TK, 128, &m13l)) != cudaSuccess) return e;
     if ((e = get_tensor_map_f16(a.w2h, TC, a.hidden, a.hidden, 128, TK, 128, &m2h)) != cudaSuccess) return e;

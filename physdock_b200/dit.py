@@ -10,9 +10,14 @@ runs in the hand-written sm_100a kernels behind include/physdock_b200.h:
 What is cached and when:
   * weights  -> re-laid-out once per parameter version (`_pack`): q|k|v concatenated, w1/w3 interleaved in blocks of 16,
     every matrix split into fp16 hi/lo planes, all 36 AdaLN-Zero linears concatenated, LayerNorm(z) affine
-    folded into linear_z.
+    folded into linear_z.  `load_state_dict`, `.to()` / `.cuda()` / `.float()` bump a version counter (O(1) check per
+    call); the full per-parameter scan runs once per complex.  After modifying a parameter IN PLACE call
+    `mark_weights_changed()`.
   * complex  -> `prepare_complex` runs once per (a, ap, s, z, masks): the pair-bias of every block
     ([6,4,Sa,Sa] + [12,16,St,St] fp32) that the reference recomputes in every block of every step.
+  * launches -> `forward` replays the ~120 kernels of one denoiser call from a CUDA graph (inputs are copied into
+    persistent buffers); the sampler uses `denoise_cond_graphed` with the conditioning of the whole schedule
+    precomputed (`conditioning_table`).
 There is no CPU / PyTorch fallback: CPU tensors raise.
 """
 from __future__ import annotations
@@ -63,11 +68,16 @@ class B200DiT(nn.Module):
         self._handle = None
         self._packed: Optional[Dict[str, torch.Tensor]] = None
         self._pack_sig = None
+        self._pack_version = -1
+        self._weights_version = 0
         self._complex_sig = None
         self._complex_keep = None
+        self._complex_token = 0
         self._workspace: Optional[torch.Tensor] = None
         self._graphs: Dict[tuple, object] = {}
         self._block_array = None
+        self._fwd_static: Dict[tuple, tuple] = {}
+        self.use_cuda_graph = True
 
     # ------------------------------------------------------------------ construction helpers
     @classmethod
@@ -97,8 +107,28 @@ class B200DiT(nn.Module):
             pass
 
     # ------------------------------------------------------------------ weights
+    def mark_weights_changed(self) -> None:
+        """Call after modifying a parameter in place (p.data.copy_(...)): forces a re-pack on the next call."""
+        self._weights_version += 1
+
+    def _apply(self, fn, *a, **kw):          # .to() / .cuda() / .float() / .half(): parameters are replaced
+        out = super()._apply(fn, *a, **kw)
+        self._weights_version += 1
+        return out
+
+    def load_state_dict(self, *a, **kw):
+        out = super().load_state_dict(*a, **kw)
+        self._weights_version += 1
+        return out
+
     def _signature(self):
         return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def _pack_fast(self) -> None:
+        """O(1) per-call check (the 319-tensor signature scan costs ~100 us of host time): re-pack only when the version
+        counter moved.  `prepare_complex` still runs the full scan once per complex."""
+        if self._packed is None or self._pack_version != self._weights_version:
+            self._pack()
 
     def _blocks_in_order(self):
         d = self.dims
@@ -122,6 +152,7 @@ class B200DiT(nn.Module):
     def _pack(self):
         sig = self._signature()
         if self._packed is not None and sig == self._pack_sig:
+            self._pack_version = self._weights_version
             return
         lib = _lib.load()
         dev = next(self.parameters()).device
@@ -195,8 +226,11 @@ class B200DiT(nn.Module):
         W.n_blocks = len(blocks)
         _lib.check(lib.pdk_dit_set_weights(self._handle, C.byref(W)), "pdk_dit_set_weights")
         self._packed, self._pack_sig, self._block_array = P, sig, blocks
+        self._pack_version = self._weights_version
         self._n_mod = n_mod
         self._complex_sig = None      # bias caches depend on the weights
+        self._complex_keep = None
+        self._graphs.clear()          # captured graphs hold pointers into the old packed weights
 
     # ------------------------------------------------------------------ per-complex cache
     def prepare_complex(self, batch: Dict[str, torch.Tensor], a: torch.Tensor, ap: torch.Tensor, s: torch.Tensor,
@@ -222,9 +256,14 @@ class B200DiT(nn.Module):
                                                _lib.ptr(apm), _lib.ptr(zm), _lib.ptr(tok_start), _lib.ptr(atom2tok),
                                                Na, Nt, _lib.ptr(bias_a), _lib.ptr(bias_t), _lib.stream_ptr(dev)),
                    "pdk_dit_prepare_complex")
-        # the handle keeps raw pointers into these
+        # the handle keeps raw pointers into a_, s_, tok_start, atom2tok and the bias caches; `sig_tensors` keeps every
+        # tensor the complex signature was taken from alive, so that a later complex cannot be handed the same addresses
+        # (which would make its signature collide with this one's)
+        self._complex_token += 1
         self._complex_keep = dict(a=a_, s=s_, tok_start=tok_start, atom2tok=atom2tok, bias_a=bias_a, bias_t=bias_t,
-                                  Na=Na, Nt=Nt)
+                                  Na=Na, Nt=Nt, token=self._complex_token,
+                                  sig_tensors=(a, ap, s, z, batch["ap_mask"], batch["z_mask"],
+                                               batch["token_id_to_chunk_sizes"], batch["atom_id_to_token_id"]))
         self._graphs.clear()
 
     @staticmethod
@@ -239,8 +278,18 @@ class B200DiT(nn.Module):
         k = self._complex_keep
         _lib.check(lib.pdk_dit_workspace_bytes(self._handle, B, k["Na"], k["Nt"], C.byref(need)), "pdk_dit_workspace_bytes")
         if self._workspace is None or self._workspace.numel() < need.value or self._workspace.device != dev:
+            # captured graphs hold raw pointers into the old buffer: drop them BEFORE it goes back to the allocator
+            self._graphs.clear()
+            self._workspace = None
             self._workspace = torch.empty(need.value, dtype=torch.uint8, device=dev)
         return self._workspace
+
+    def _check_device(self, t: torch.Tensor) -> None:
+        if not t.is_cuda:
+            raise _lib.PdkError("physdock_b200 kernels need CUDA tensors (no CPU fallback)")
+        if t.device.index != torch.cuda.current_device():
+            raise _lib.PdkError(f"tensor lives on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()}: "
+                                "wrap the call in torch.cuda.device(...) (one process per GPU is the intended use)")
 
     # ------------------------------------------------------------------ AF3DiT.forward
     def denoise(self, x_hat: torch.Tensor, t_hat: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -248,6 +297,7 @@ class B200DiT(nn.Module):
         if self._complex_keep is None:
             raise _lib.PdkError("prepare_complex() has not been called")
         lib = _lib.load()
+        self._check_device(x_hat)
         B = x_hat.shape[0]
         dev = x_hat.device
         x_hat = x_hat.float().contiguous()
@@ -261,41 +311,129 @@ class B200DiT(nn.Module):
                                        _lib.ptr(out), _lib.stream_ptr(dev)), "pdk_dit_denoise")
         return out
 
-    def denoise_graphed(self, x_hat: torch.Tensor, t_hat: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
-        """`denoise` replayed from a CUDA graph (one graph per set of argument buffers and prepared complex).
+    def _graph_key(self, *tensors):
+        return tuple(0 if t is None else t.data_ptr() for t in tensors) + (tuple(tensors[0].shape), self._complex_keep["token"],
+                                                                            self._pack_version, self._workspace.data_ptr())
 
-        The call enqueues ~136 kernels whose arguments are all pointers into persistent buffers, so the whole
-        denoiser is captured once and replayed with a single launch; x_hat / t_hat / out must be persistent
-        tensors that the caller updates in place (DiffusionSampler does)."""
-        if not (x_hat.is_contiguous() and t_hat.is_contiguous() and out.is_contiguous()
-                and x_hat.dtype == t_hat.dtype == out.dtype == torch.float32):
-            return self.denoise(x_hat, t_hat, out)
-        key = (x_hat.data_ptr(), t_hat.data_ptr(), out.data_ptr(), tuple(x_hat.shape), id(self._complex_keep),
-               self._pack_sig is not None and hash(self._pack_sig))
+    def _replay(self, key, enqueue):
+        """Runs `enqueue()` (which only enqueues library calls with persistent pointer arguments) from a CUDA graph."""
         g = self._graphs.get(key)
         if g is None:
-            self.denoise(x_hat, t_hat, out)          # warm-up: workspace, tensor maps, function attributes
-            torch.cuda.synchronize(x_hat.device)
-            if len(self._graphs) > 8:
+            enqueue()                                 # warm-up: tensor maps, function attributes
+            torch.cuda.synchronize()
+            if len(self._graphs) > 16:
                 self._graphs.clear()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                self.denoise(x_hat, t_hat, out)
+                enqueue()
             self._graphs[key] = g
         g.replay()
+
+    def denoise_graphed(self, x_hat: torch.Tensor, t_hat: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+        """`denoise` replayed from a CUDA graph (one graph per set of argument buffers, workspace and prepared complex).
+
+        The call enqueues ~124 kernels whose arguments are all pointers into persistent buffers, so the whole
+        denoiser is captured once and replayed with a single launch; x_hat / t_hat / out must be persistent
+        tensors that the caller updates in place."""
+        if not (x_hat.is_contiguous() and t_hat.is_contiguous() and out.is_contiguous()
+                and x_hat.dtype == t_hat.dtype == out.dtype == torch.float32) or not self.use_cuda_graph:
+            return self.denoise(x_hat, t_hat, out)
+        self._ensure_workspace(x_hat.shape[0], x_hat.device)
+        self._replay(self._graph_key(x_hat, t_hat, out), lambda: self.denoise(x_hat, t_hat, out))
+        return out
+
+    # ------------------------------------------------------------------ conditioning hoisted out of the step
+    def cond_width(self) -> int:
+        self._pack_fast()
+        return int(_lib.load().pdk_dit_cond_width(self._handle))
+
+    def conditioning_table(self, t_hat: torch.Tensor) -> torch.Tensor:
+        """Rows [modulations (n_mod) | c_in, c_skip, c_out, t_hat | t_next, eta, 0, 0] for every noise level of `t_hat` [n]
+        (fp32, CUDA): everything AF3DiT derives from t_hat alone, computed once per schedule instead of once per step.
+        Returns a [n, cond_width] view of the table; entries 4..7 of the coefficient block are left for the caller."""
+        self._pack_fast()
+        lib = _lib.load()
+        t_hat = t_hat.float().contiguous()
+        self._check_device(t_hat)
+        n, dev, width = t_hat.numel(), t_hat.device, self.cond_width()
+        need = C.c_size_t()
+        _lib.check(lib.pdk_dit_conditioning_workspace_bytes(self._handle, n, C.byref(need)), "pdk_dit_conditioning_workspace_bytes")
+        ws = torch.empty(need.value, dtype=torch.uint8, device=dev)
+        table = torch.zeros(int(lib.pdk_pad_len(n)), width, dtype=torch.float32, device=dev)
+        _lib.check(lib.pdk_dit_conditioning(self._handle, _lib.ptr(t_hat), n, _lib.ptr(ws), ws.numel(), _lib.ptr(table), width,
+                                            _lib.stream_ptr(dev)), "pdk_dit_conditioning")
+        ws.record_stream(torch.cuda.current_stream(dev))
+        return table[:n]
+
+    def denoise_cond(self, x_hat: torch.Tensor, cond: torch.Tensor, out: torch.Tensor,
+                     x_next: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """AF3DiT for the prepared complex with precomputed conditioning: `cond` is one row [cond_width] shared by all
+        samples, or [B, cond_width].  With `x_next` the physics-free Euler update is written by the last kernel."""
+        if self._complex_keep is None:
+            raise _lib.PdkError("prepare_complex() has not been called")
+        lib = _lib.load()
+        self._check_device(x_hat)
+        B, dev = x_hat.shape[0], x_hat.device
+        if cond.dim() == 1:
+            stride = 0
+        else:
+            if cond.shape[0] != B:
+                raise _lib.PdkError("cond must be one row or one row per sample")
+            stride = cond.stride(0)
+        if cond.stride(-1) != 1 or cond.shape[-1] != self.cond_width() or cond.dtype != torch.float32:
+            raise _lib.PdkError("cond rows must be contiguous fp32 of width cond_width()")
+        if x_hat.shape[1] != self._complex_keep["Na"] or not x_hat.is_contiguous() or x_hat.dtype != torch.float32:
+            raise _lib.PdkError("x_hat must be contiguous fp32 [B, Na, 3] of the prepared complex")
+        ws = self._ensure_workspace(B, dev)
+        _lib.check(lib.pdk_dit_denoise_cond(self._handle, x_hat.data_ptr(), cond.data_ptr(), stride, B, _lib.ptr(ws), ws.numel(),
+                                            _lib.ptr(out), _lib.ptr(x_next), _lib.stream_ptr(dev)), "pdk_dit_denoise_cond")
+        return out
+
+    def denoise_cond_graphed(self, x_hat, cond, out, x_next=None):
+        """`denoise_cond` replayed from a CUDA graph; all four tensors must be persistent buffers updated in place."""
+        if not self.use_cuda_graph:
+            return self.denoise_cond(x_hat, cond, out, x_next)
+        self._ensure_workspace(x_hat.shape[0], x_hat.device)
+        self._replay(self._graph_key(x_hat, cond, out, x_next), lambda: self.denoise_cond(x_hat, cond, out, x_next))
         return out
 
     def forward(self, batch: Dict[str, torch.Tensor], x_hat: torch.Tensor, t_hat: torch.Tensor, a: torch.Tensor,
                 ap: torch.Tensor, s: torch.Tensor, z: torch.Tensor) -> torch.Tensor:
         """Same contract as AF3DiT.forward (transformers.py:235-262); leading batch dims other than the
-        sample dimension are not supported (the reference sampler never uses them)."""
-        self._pack()
+        sample dimension are not supported (the reference sampler never uses them).
+
+        This is the call the reference sampler makes every step through `partial(self.dit, batch=..., a=..., ap=..., s=...,
+        z=...)(x_hat=..., t_hat=...)` (model.py:153,221): inputs are copied into persistent buffers, the denoiser is
+        replayed from a CUDA graph, and a fresh tensor is returned."""
+        self._pack_fast()
         sig = self._complex_signature(batch, a, ap, s, z)
         if sig != self._complex_sig:
+            self._pack()                      # full parameter scan, once per complex
             self.prepare_complex(batch, a, ap, s, z)
             self._complex_sig = sig
-        return self.denoise(x_hat, t_hat)
+        self._check_device(x_hat)
+        B = x_hat.shape[0]
+        t_hat = t_hat.to(device=x_hat.device, dtype=torch.float32).reshape(-1)
+        if t_hat.numel() == 1 and B > 1:
+            t_hat = t_hat.expand(B)
+        if not self.use_cuda_graph or torch.cuda.is_current_stream_capturing():
+            return self.denoise(x_hat, t_hat)
+        key = (B, x_hat.shape[1], x_hat.device.index)
+        st = self._fwd_static.get(key)
+        if st is None:
+            if len(self._fwd_static) > 4:
+                self._fwd_static.clear()
+            st = self._fwd_static[key] = (torch.empty(B, x_hat.shape[1], 3, dtype=torch.float32, device=x_hat.device),
+                                          torch.empty(B, dtype=torch.float32, device=x_hat.device),
+                                          torch.empty(B, x_hat.shape[1], 3, dtype=torch.float32, device=x_hat.device))
+        xs, ts, outs = st
+        xs.copy_(x_hat)
+        ts.copy_(t_hat)
+        self.denoise_graphed(xs, ts, outs)
+        return outs.clone()
 
-    def launches_per_denoise(self) -> int:
-        self._pack()
-        return int(_lib.load().pdk_dit_launches_per_denoise(self._handle))
+    def launches_per_denoise(self, cond: bool = False) -> int:
+        """Kernels per denoiser call (`cond`: with the conditioning precomputed, as the sampler runs it)."""
+        self._pack_fast()
+        lib = _lib.load()
+        return int((lib.pdk_dit_launches_per_denoise_cond if cond else lib.pdk_dit_launches_per_denoise)(self._handle))

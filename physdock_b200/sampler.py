@@ -2,11 +2,13 @@
 (reference PhysDock/models/model.py:157-282) and of the module surface `PhysDock` exposes to
 redocking.py:284-299 / screening.py:294.
 
-Per step (model.py:211-281) the device work is four library calls, no host<->device sync:
-    pdk_centre_augment  (centre_random_augmentation + diffuse, fused)
-    pdk_dit_denoise     (AF3DiT)
-    [pdk_template_select + pdk_rigid_align]      (physics guidance, RDKit-free part)
-    pdk_euler_update
+Per step (model.py:211-281) the device work is, with no host<->device sync:
+    pdk_centre_augment    (centre_random_augmentation + diffuse, fused)
+    pdk_dit_denoise_cond  (AF3DiT; its last kernel also writes the Euler update when the step has no physics guidance)
+    [pdk_template_select + pdk_rigid_align + pdk_euler_update]      (physics guidance, RDKit-free part)
+Everything the denoiser derives from the noise level alone (time embedding, the 36 AdaLN-Zero modulations, c_in / c_skip /
+c_out) is computed for the WHOLE schedule when the sampler is built (`B200DiT.conditioning_table`): all samples of a step
+share one noise level, known before the loop starts.
 The noise schedule lives on the host exactly as in the reference (`karras_noise_schedule` runs on the CPU,
 model.py:147), so the `t_cur > gamma_min` branches are taken on host floats instead of syncing on a device
 scalar each step (model.py:213).  Random numbers are drawn with the same torch calls, shapes, dtypes and
@@ -15,7 +17,6 @@ on the same device type under the same `torch.manual_seed`.
 """
 from __future__ import annotations
 
-import os
 from typing import Callable, Dict, List, Optional
 
 import torch
@@ -147,7 +148,7 @@ class DiffusionSampler:
                  use_cuda_graph: bool = True, physics_field=None, physics_step: float = 0.002,
                  physics_gmax: float = 50.0):
         dev = batch["x_gt"].device
-        self.use_cuda_graph = use_cuda_graph and os.environ.get("PDK_NO_GRAPH") is None
+        self.use_cuda_graph = use_cuda_graph
         if dev.type != "cuda":
             raise _lib.PdkError("sample_diffusion needs the batch on a CUDA device (no CPU fallback)")
         self.dit, self.dev, self.B, self.Na = dit, dev, num_sample, batch["x_gt"].shape[-2]
@@ -181,8 +182,10 @@ class DiffusionSampler:
         if sig != dit._complex_sig:
             dit.prepare_complex(batch, a, ap, s, z)
             dit._complex_sig = sig
+        self.steps = steps
         self.sigmas = karras_noise_schedule(num_steps=steps, p=karras_noise_schedule_power)     # host, fp32
         shape = (self.B, self.Na, 3)
+        # persistent buffers: every kernel argument of a step is a pointer into these (CUDA-graph replay)
         self.x_next = torch.empty(shape, dtype=torch.float32, device=dev)
         self.x_hat, self.x_den, self.aligned = (torch.empty_like(self.x_next) for _ in range(3))
         self.t_hat_dev = torch.empty(self.B, dtype=torch.float32, device=dev)
@@ -190,10 +193,20 @@ class DiffusionSampler:
         self._sched_cache: Dict[int, tuple] = {}
         self._copy_stream = None
         self._sched_floats: Dict[int, tuple] = {}
+        # conditioning of the whole schedule (2 launches, once): row i = [modulations | c_in c_skip c_out t_hat | t_next eta . .]
+        t_hats = torch.stack([self.schedule(i)[2].float() for i in range(steps)]).to(dev)
+        self.cond_table = dit.conditioning_table(t_hats)
+        n_mod = dit.cond_width() - 8
+        extra = torch.zeros(steps, 2, dtype=torch.float32)
+        for i in range(steps):
+            _, t_next, _, stochastic, _ = self.schedule(i)
+            extra[i, 0], extra[i, 1] = t_next, (self.eta_s if stochastic else self.eta_d)
+        self.cond_table[:, n_mod + 4:n_mod + 6] = extra.to(dev)
+        self.cond_cur = torch.empty(dit.cond_width(), dtype=torch.float32, device=dev)
 
     def begin(self) -> torch.Tensor:
         """x_0 = sigma_0 * N(0,1)   (prepare_solver, model.py:148)."""
-        self.x_next = (self.sigmas[0].to(self.dev) * self.rng.normal((self.B, self.Na, 3))).contiguous()
+        self.x_next.copy_(self.sigmas[0].to(self.dev) * self.rng.normal((self.B, self.Na, 3)))
         return self.x_next
 
     def schedule(self, i: int):
@@ -223,8 +236,23 @@ class DiffusionSampler:
         noise = self.rng.normal((self.B, self.Na, 3)) if stochastic else None
         return u4, trans, noise
 
+    def launches_per_step(self, i: int) -> int:
+        """Kernels of THIS library enqueued by step(i) (torch's own random draws / copies not counted)."""
+        thr = self.gamma_min * self.mmff_factor
+        t_cur = self.sigmas[i]
+        early, late = bool(t_cur > thr), bool(t_cur <= thr)
+        n = 1 + self.dit.launches_per_denoise(cond=True)
+        if self.align_ref_pos and early:
+            n += (2 if self.ref_mol_poses is not None else 0) + 2              # template eps + pick, rigid align, euler
+        elif late and self.physics_field is not None:
+            n += self.physics_field.launches_per_descend(self.mmff_iters) + 2
+        elif late and self.mmff_fn is not None:
+            n += 2
+        return n
+
     def step(self, i: int, randoms=None, teacher_x_hat: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """One iteration of the loop at schedule index i; returns (and stores) x_next."""
+        """One iteration of the loop at schedule index i; returns x_next (a persistent buffer, updated in place by the
+        following step: clone it to keep it)."""
         t_cur, t_next, t_hat, stochastic, noise_scale = self.schedule(i)
         fl = self._sched_floats.get(i)
         if fl is None:       # python floats of the step's scalars + the two branch conditions, computed once per index
@@ -232,15 +260,22 @@ class DiffusionSampler:
             fl = self._sched_floats[i] = (float(t_hat), float(t_next), bool(t_cur > thr), bool(t_cur <= thr))
         t_hat_f, t_next_f, early, late = fl
         u4, trans, noise = randoms if randoms is not None else self.draw(i)
-        self.t_hat_dev.fill_(t_hat_f)
         centre_augment_noise(self.x_next, self.x_exists, u4, trans, noise, self.lam, noise_scale, out=self.x_hat)
         if teacher_x_hat is not None:
             self.x_hat.copy_(teacher_x_hat)
+        # does this step blend a physics direction into d_cur (model.py:223-261)?  If not, the denoiser's last kernel also
+        # writes the Euler update (x_next is dead once centre_augment has consumed it, so it is updated in place).
+        guided = (self.align_ref_pos and early) or (late and (self.physics_field is not None or self.mmff_fn is not None))
+        fused_next = None if guided else self.x_next
         if self.use_cuda_graph:
-            self.dit.denoise_graphed(self.x_hat, self.t_hat_dev, self.x_den)
+            self.cond_cur.copy_(self.cond_table[i])          # one 166 KB device copy selects the step's conditioning
+            self.dit.denoise_cond_graphed(self.x_hat, self.cond_cur, self.x_den, fused_next)
         else:
-            self.dit.denoise(self.x_hat, self.t_hat_dev, out=self.x_den)
+            self.dit.denoise_cond(self.x_hat, self.cond_table[i], self.x_den, fused_next)
         self.last_used = None
+        if not guided:
+            return self.x_next
+        self.t_hat_dev.fill_(t_hat_f)
         physics = False
         if self.align_ref_pos and early:
             if self.ref_mol_poses is not None:
@@ -260,11 +295,9 @@ class DiffusionSampler:
             weighted_rigid_align(self.x_den, self.x_exists, x_ref, self.weights, out=self.aligned)
             physics = True
         eta = self.eta_s if stochastic else self.eta_d
-        x_new = torch.empty_like(self.x_next)
         euler_update(self.x_hat, self.x_den, self.t_hat_dev, t_next_f, eta, self.aligned if physics else None,
-                     self.weights if physics else None, out=x_new)
-        self.x_next = x_new
-        return x_new
+                     self.weights if physics else None, out=self.x_next)
+        return self.x_next
 
     def upload_randoms(self, i: int, u4_host, trans_host, noise_host):
         """H2D of step i's random tensors (pinned host memory) on a separate copy stream, so that it overlaps the

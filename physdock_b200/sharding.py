@@ -8,7 +8,7 @@ drawing everything.
 """
 from __future__ import annotations
 
-from typing import Tuple
+from typing import Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
@@ -27,21 +27,48 @@ def shard_range(num_sample: int, rank: int, world_size: int) -> Tuple[int, int]:
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def gather_samples(x_local: torch.Tensor) -> torch.Tensor:
-    """all_gather along the sample axis (ragged shards allowed).  NCCL on GPUs, gloo in the CPU tests."""
+def warm_communicator(device=None) -> None:
+    """Creates the communicator (NCCL: lazy, ~ms on first use) outside any timed or latency-critical region."""
+    rank, ws = world()
+    if ws == 1:
+        return
+    t = torch.zeros(1, device=device if device is not None else "cpu")
+    dist.all_reduce(t)
+    if t.is_cuda:
+        torch.cuda.synchronize(t.device)
+
+
+def gather_samples(x_local: torch.Tensor, counts: Optional[Sequence[int]] = None) -> torch.Tensor:
+    """all_gather along the sample axis (ragged and empty shards allowed).  NCCL on GPUs, gloo in the CPU tests.
+
+    `counts` = samples per rank when the caller knows them on the host (`shard_range` does): ONE
+    `all_gather_into_tensor` of the padded shards, no count exchange and no host sync.  Without it the counts are
+    exchanged first (one extra small collective and a device->host read)."""
     rank, ws = world()
     if ws == 1:
         return x_local
-    n = torch.tensor([x_local.shape[0]], device=x_local.device, dtype=torch.int64)
-    counts = [torch.zeros_like(n) for _ in range(ws)]
-    dist.all_gather(counts, n)
-    counts = [int(c) for c in counts]
+    if counts is None:
+        n = torch.tensor([x_local.shape[0]], device=x_local.device, dtype=torch.int64)
+        allc = torch.empty(ws, device=x_local.device, dtype=torch.int64)
+        dist.all_gather_into_tensor(allc, n)
+        counts = [int(c) for c in allc.tolist()]
+    counts = list(counts)
+    assert len(counts) == ws and counts[rank] == x_local.shape[0], (counts, rank, tuple(x_local.shape))
     m = max(counts)
-    pad = torch.zeros((m,) + tuple(x_local.shape[1:]), dtype=x_local.dtype, device=x_local.device)
-    pad[: x_local.shape[0]] = x_local
-    bufs = [torch.empty_like(pad) for _ in range(ws)]
-    dist.all_gather(bufs, pad)
-    return torch.cat([b[:c] for b, c in zip(bufs, counts)], dim=0)
+    tail = tuple(x_local.shape[1:])
+    if m == 0:
+        return x_local.new_zeros((0,) + tail)
+    if all(c == m for c in counts):
+        send = x_local.contiguous()
+    else:
+        send = x_local.new_zeros((m,) + tail)
+        send[: x_local.shape[0]] = x_local
+    out = x_local.new_empty((ws * m,) + tail)
+    dist.all_gather_into_tensor(out, send)
+    if all(c == m for c in counts):
+        return out
+    out = out.view((ws, m) + tail)
+    return torch.cat([out[r, :c] for r, c in enumerate(counts)], dim=0)
 
 
 class ShardedRNG:
@@ -78,10 +105,12 @@ def sample_diffusion_sharded(dit, batch, a, ap, s, z, num_sample: int, seed: int
     else:
         torch.manual_seed(seed + rank)
         rng = DeviceRNG(dev)
-    if kw.get("ref_mol_poses") is not None:
-        pass    # templates are shared by all samples: nothing to shard
-    x_local = sample_diffusion(dit, batch, a, ap, s, z, num_sample=hi - lo, rng=rng, **kw)
-    return gather_samples(x_local)
+    counts = [shard_range(num_sample, r, ws)[1] - shard_range(num_sample, r, ws)[0] for r in range(ws)]
+    if hi > lo:
+        x_local = sample_diffusion(dit, batch, a, ap, s, z, num_sample=hi - lo, rng=rng, **kw)
+    else:       # num_sample < world_size: this rank has nothing to sample but still takes part in the collective
+        x_local = torch.zeros(0, batch["x_gt"].shape[-2], 3, dtype=torch.float32, device=dev)
+    return gather_samples(x_local, counts)
 
 
 # ---------------------------------------------------------------------------------------------------------------------

@@ -75,3 +75,14 @@ def _log(name, err, tol, scale):
 
 def log_value(name, value):
     _log(name, float(value), float("nan"), float("nan"))
+
+
+def c1_fixture():
+    """BASELINE.json configs[0] on real data (tests/golden/c1_5sd5.npz, oracle/make_golden_r02.py): the batch keys the hot
+    path reads, the (fp16-stored) reference trunk outputs, reference AF3DiT outputs and a 12-step sampler trace."""
+    if "c1" not in _cache:
+        g = load_npz("c1_5sd5.npz")
+        batch = {k[len("batch_"):]: T(g[k]) for k in g if k.startswith("batch_")}
+        cond = {k: T(g[k]).float() for k in ("a", "ap", "s", "z")}
+        _cache["c1"] = (g, batch, cond)
+    return _cache["c1"]

@@ -1,7 +1,6 @@
-"""Thin Python wrappers over the op-level C entry points (pdk_op_*), one kernel each.
-
-They exist so the parity tests can check every kernel against the oracle in isolation; the product path
-(`B200DiT.denoise`) drives the same launchers from C++ in a single call.
+"""TEST HARNESS (not part of the product package): thin Python wrappers over the op-level C entry points (pdk_op_*), one
+kernel each, so that the parity tests (and the timing tools under tools/) can drive every kernel in isolation through the
+C ABI.  The product path (`B200DiT.denoise*`) drives the same launchers from C++ in a single call.
 """
 from __future__ import annotations
 
@@ -10,7 +9,7 @@ from typing import Optional, Tuple
 
 import torch
 
-from . import _lib
+from physdock_b200 import _lib
 
 LOG2E = 1.4426950408889634
 

@@ -30,7 +30,8 @@ def test_header_symbols_all_exported_and_bound(lib):
 
 
 def test_host_only_entry_points(lib):
-    assert lib.pdk_abi_version() == 1
+    from physdock_b200 import _lib
+    assert lib.pdk_abi_version() == _lib.ABI_VERSION == 2
     assert lib.pdk_pad_len(2048) == 2048 and lib.pdk_pad_len(1325) == 1408 and lib.pdk_pad_len(1) == 128
 
 
@@ -47,6 +48,12 @@ def test_handle_lifecycle_and_sizes_without_gpu(lib):
     assert lib.pdk_dit_workspace_bytes(h, 16, 2048, 256, C.byref(ws)) == 0
     assert 100e6 < ws.value < 2e9
     assert lib.pdk_dit_launches_per_denoise(h) == 3 + 5 * 6 + 7 * 12 + 7     # atom transition fused
+    assert lib.pdk_dit_launches_per_denoise_cond(h) == 1 + 5 * 6 + 7 * 12 + 7     # conditioning hoisted out of the step
+    assert lib.pdk_dit_cond_width(h) == 41472 + 8
+    cb = C.c_size_t()
+    assert lib.pdk_dit_conditioning_workspace_bytes(h, 40, C.byref(cb)) == 0 and cb.value == 2 * 128 * 256 * 2
+    assert lib.pdk_dit_denoise_cond(h, None, None, 0, 1, None, 0, None, None, None) != 0
+    assert b"no prepared complex" in lib.pdk_last_error()
     # errors are reported, not swallowed
     assert lib.pdk_dit_denoise(h, None, None, 1, None, 0, None, None) != 0
     assert b"no prepared complex" in lib.pdk_last_error()

@@ -35,7 +35,7 @@ def pad_rows(x, S_pad):
 # ------------------------------------------------------------------------------------- GEMM / attention core
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 384, 128), (384, 128, 1408), (128, 512, 512), (2048, 256, 192)])
 def test_gemm_store_vs_fp64(M, N, K):
-    from physdock_b200 import ops
+    from tests import pdk_ops as ops
     g = torch.Generator().manual_seed(M + N + K)
     A = (torch.randn(M, K, generator=g) * 3).to(DEV)
     W = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(DEV)
@@ -54,7 +54,7 @@ def test_gemm_store_vs_fp64(M, N, K):
 
 @pytest.mark.parametrize("B,H,S", [(1, 4, 128), (2, 4, 384), (2, 16, 256), (5, 4, 256), (7, 16, 128), (9, 4, 640)])
 def test_attention_vs_fp64(B, H, S):
-    from physdock_b200 import ops
+    from tests import pdk_ops as ops
     g = torch.Generator().manual_seed(B * 1000 + S)
     q, k, v = [torch.randn(B, H, S, 32, generator=g).to(DEV) * s for s in (2.0, 2.0, 1.0)]
     bias = (torch.randn(H, S, S, generator=g) * 2).to(DEV)
@@ -70,7 +70,7 @@ def test_attention_vs_fp64(B, H, S):
 def test_attention_many_samples_chunked_work_list():
     """BASELINE.json configs[2]-sized call (Na = 3072, dozens of samples): the work list no longer fits the kernel
     parameters and launch_attention splits the samples into several launches (attention_umma.cu: kMaxWork)."""
-    from physdock_b200 import ops
+    from tests import pdk_ops as ops
     B, H, S = 40, 4, 3072
     g = torch.Generator(device=DEV).manual_seed(77)
     q, k, v = [torch.randn(B, H, S, 32, generator=g, device=DEV) * s for s in (2.0, 2.0, 1.0)]
@@ -89,7 +89,7 @@ def test_attention_many_samples_chunked_work_list():
 
 # ------------------------------------------------------------------------------------- conditioning
 def test_time_embed_and_coef(env):
-    from physdock_b200 import ops
+    from tests import pdk_ops as ops
     dims, sd, dit, k = env
     P = dit._packed
     tsilu, coef = ops.time_embed(k["k_t_hat"], P["freq"], P["te_w1"], P["te_b1"], P["te_w2"], P["te_b2"], 16.0)
@@ -101,7 +101,7 @@ def test_time_embed_and_coef(env):
 
 
 def test_mod_gemv_and_adaln(env):
-    from physdock_b200 import ops
+    from tests import pdk_ops as ops
     dims, sd, dit, k = env
     P = dit._packed
     tsilu = F.silu(k["t_emb"])
@@ -117,7 +117,7 @@ def test_mod_gemv_and_adaln(env):
 
 
 def test_pair_bias_atom_and_token(env):
-    from physdock_b200 import ops
+    from tests import pdk_ops as ops
     dims, sd, dit, k = env
     P = dit._packed
     for name, pair, mask, wT, bz, stack, bi_local, H in (
@@ -134,7 +134,7 @@ def test_pair_bias_atom_and_token(env):
 
 # ------------------------------------------------------------------------------------- whole sub-blocks
 def run_attention_block(dit, dims, k, bi, x, pair, mask, wT, bz, bi_local, S):
-    from physdock_b200 import ops
+    from tests import pdk_ops as ops
     P = dit._packed
     B, _, c = x.shape
     H = c // 32
@@ -157,7 +157,7 @@ def test_qkv_epilogue(env):
     dims, sd, dit, k = env
     P = dit._packed
     _, planes = run_attention_block(dit, dims, k, ATOM_BI, k["ba"], k["ap"], k["ap_mask"], P["wz_atom_T"], P["bz_atom"], 1, 75)
-    from physdock_b200 import ops
+    from tests import pdk_ops as ops
     p = "atom_dit_encoder.blocks.1.attention."
     xn, _ = O.ada_layer_norm_zero(sd, p + "norm_s.", k["ba"], k["t_emb"], dims.eps)
     want = {}
@@ -194,7 +194,7 @@ def test_token_attention_block(env, mask_key, out_key):
 
 @pytest.mark.parametrize("bi,xk,outk,S", [(ATOM_BI, "ba", "atom_trans_out", 75), (TOK_BI, "bs", "tok_trans_out", 37)])
 def test_transition_block(env, bi, xk, outk, S):
-    from physdock_b200 import ops
+    from tests import pdk_ops as ops
     dims, sd, dit, k = env
     P = dit._packed
     x = k[xk]
@@ -211,7 +211,7 @@ def test_transition_block(env, bi, xk, outk, S):
 
 def test_fused_atom_transition_vs_oracle_and_unfused(env):
     """transition_umma.cu (one kernel) against the oracle KAT and against the three-kernel path it replaces."""
-    from physdock_b200 import ops
+    from tests import pdk_ops as ops
     dims, sd, dit, k = env
     P = dit._packed
     bi, x = ATOM_BI, k["ba"]
@@ -244,7 +244,7 @@ def test_fused_atom_transition_vs_oracle_and_unfused(env):
 
 # ------------------------------------------------------------------------------------- glue
 def test_precond_downscale_upscale_denoise(env):
-    from physdock_b200 import ops
+    from tests import pdk_ops as ops
     dims, sd, dit, k = env
     P = dit._packed
     _, coef = ops.time_embed(k["k_t_hat"], P["freq"], P["te_w1"], P["te_b1"], P["te_w2"], P["te_b2"], 16.0)

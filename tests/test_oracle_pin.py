@@ -88,6 +88,55 @@ def test_oracle_sampler_replays_reference_trace(name):
     assert float(O.rmsd(x, T(g["x_final"])).max()) < 1e-4
 
 
+@pytest.mark.parametrize("name", ["nophys", "templates"])
+def test_oracle_replays_full_40_step_reference_trace(name):
+    """The FULL redocking schedule (steps=40, rho=1000: 29 stochastic steps + the 11-step ODE tail), recorded from the real
+    reference by oracle/make_golden_r02.py."""
+    dims, sd, sd_sum = medium_state()
+    cx = complex_64_512()
+    g = load_npz(f"trace40_{name}.npz")
+    assert sd_sum == float(g["sd_checksum"]) and checksum(cx["ap"]) == float(g["ap_checksum"])
+    tape = [T(g[f"tape_{i}"]) for i in range(int(g["n_tape"]))]
+    kw = dict(nophys=dict(align_ref_pos=False),
+              templates=dict(align_ref_pos=True, ref_mol_poses=make_templates(cx, 12), mmff_gamma_0_factor=6.0))[name]
+    trace = []
+    rng = O.ReplayRNG(tape)
+    x = O.sample_diffusion(sd, cx, cx["a"], cx["ap"], cx["s"], cx["z"], num_sample=2, steps=40,
+                           karras_noise_schedule_power=1000, rng=rng, trace=trace, **kw)
+    assert rng.pos == len(tape) and len(trace) == 40
+    assert sum(1 for st in trace if st["t_cur"] > 1.0) == 29
+    for i, st in enumerate(trace):
+        assert torch.equal(st["t_hat"], T(g[f"t_hat_{i}"])), i
+        assert float(O.rmsd(st["x_hat"], T(g[f"x_hat_{i}"])).max()) < 1e-4, i
+        assert float(O.rmsd(st["x_denoised"], T(g[f"x_denoised_{i}"])).max()) < 1e-4, i
+    assert float(O.rmsd(x, T(g["x_final"])).max()) < 1e-4
+
+
+def test_oracle_on_real_data_c1_fixture():
+    """BASELINE.json configs[0]: real FeatureLoader output of 5SD5_HWI (Nt=64, Na=318, 29 ligand atoms, ragged chunks)."""
+    from tests.helpers import c1_fixture
+    dims, sd, sd_sum = medium_state()
+    g, batch, cond = c1_fixture()
+    assert sd_sum == float(g["sd_checksum"])
+    Nt, Na = int(g["Nt"]), int(g["Na"])
+    assert (Nt, Na) == (64, 318) and batch["atom_id_to_token_id"].shape == (Na,)
+    assert int(batch["token_id_to_chunk_sizes"].sum()) == Na and int(batch["token_id_to_chunk_sizes"].max()) > 1
+    assert int(batch["is_ligand"][batch["atom_id_to_token_id"]].sum()) == 29
+    for t in T_LEVELS:
+        with torch.no_grad():
+            y = O.af3dit_forward(sd, batch, T(g[f"x_hat_{t}"]), torch.full([4], t), cond["a"], cond["ap"], cond["s"], cond["z"])
+        assert float(O.rmsd(y, T(g[f"x_denoised_{t}"])).max()) < 2e-5, t
+    tape = [T(g[f"trace_tape_{i}"]) for i in range(int(g["trace_n_tape"]))]
+    trace = []
+    rng = O.ReplayRNG(tape)
+    x = O.sample_diffusion(sd, batch, cond["a"], cond["ap"], cond["s"], cond["z"], num_sample=4, steps=12,
+                           karras_noise_schedule_power=1000, rng=rng, trace=trace, align_ref_pos=True)
+    assert rng.pos == len(tape)
+    for i, st in enumerate(trace):
+        assert float(O.rmsd(st["x_denoised"], T(g[f"trace_x_denoised_{i}"])).max()) < 1e-4, i
+    assert float(O.rmsd(x, T(g["trace_x_final"])).max()) < 1e-4
+
+
 def test_schedule_facts():
     """rho=1000, 40 steps => 29 stochastic steps (t_cur>1), 17 with t_cur<=6."""
     s = O.karras_noise_schedule(40, p=1000)

@@ -35,7 +35,18 @@ def _worker(rank, ws, port, q):
     x0 = rng.normal((hi - lo, 7, 3))         # the per-rank slice of one global draw
     u = rng.rand((hi - lo,))
     local = x0 * 2 + u[:, None, None]        # stand-in for the per-sample computation
-    full = gather_samples(local)
+    full = gather_samples(local)             # counts exchanged
+    counts = [shard_range(n, r, ws)[1] - shard_range(n, r, ws)[0] for r in range(ws)]
+    full_known = gather_samples(local, counts)      # host-known counts: one collective
+    assert torch.equal(full, full_known)
+    # equal shards (no padding path) and an empty shard (num_sample < world_size)
+    eq = gather_samples(torch.full((2, 3), float(rank)), [2, 2])
+    assert torch.equal(eq, torch.tensor([[0.] * 3] * 2 + [[1.] * 3] * 2))
+    lo1, hi1 = shard_range(1, rank, ws)
+    one = gather_samples(torch.full((hi1 - lo1, 4, 3), 7.0), [1, 0])
+    assert one.shape == (1, 4, 3) and bool((one == 7.0).all())
+    none = gather_samples(torch.zeros(0, 4, 3), [0, 0])
+    assert none.shape == (0, 4, 3)
     if rank == 0:
         q.put(full)
     dist.barrier()

@@ -1,7 +1,7 @@
 """Runs the atom-shaped attention kernel a few times (for ncu captures): B=16, H=4, S=2048."""
 import sys, os, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from physdock_b200 import ops
+from tests import pdk_ops as ops
 B, H, S = int(os.environ.get("B", 16)), int(os.environ.get("H", 4)), int(os.environ.get("S", 2048))
 dev = torch.device("cuda")
 g = torch.Generator(device=dev).manual_seed(0)

@@ -1,7 +1,7 @@
 """Runs the atom- and token-shaped QKV GEMMs a few times (for ncu captures)."""
 import sys, os, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from physdock_b200 import ops
+from tests import pdk_ops as ops
 dev = torch.device("cuda")
 g = torch.Generator(device=dev).manual_seed(0)
 def planes(r, c): return ops.split_planes(torch.randn(r, c, generator=g, device=dev))

@@ -1,7 +1,7 @@
 """Graph-timed atom- and token-shaped attention launches (us per launch, best of 5 replays of 12 launches)."""
 import sys, os, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from physdock_b200 import ops
+from tests import pdk_ops as ops
 dev = torch.device("cuda")
 g = torch.Generator(device=dev).manual_seed(0)
 def run(B, H, S, n=12):

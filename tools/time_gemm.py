@@ -1,7 +1,7 @@
 """CUDA-event timing of the GEMM shapes of one atom block and one token block (B=16): us per launch."""
 import sys, os, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from physdock_b200 import ops
+from tests import pdk_ops as ops
 dev = torch.device("cuda")
 g = torch.Generator(device=dev).manual_seed(0)
 def planes(r, c):

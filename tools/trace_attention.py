@@ -1,7 +1,8 @@
 """Per-unit timeline of one CTA of the attention kernel (debug).  Prints cycle stamps relative to the first."""
 import sys, os, ctypes, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from physdock_b200 import ops, _lib
+from physdock_b200 import _lib
+from tests import pdk_ops as ops
 B, H, S = 16, 4, 2048
 dev = torch.device("cuda")
 g = torch.Generator(device=dev).manual_seed(0)
