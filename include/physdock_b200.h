@@ -166,6 +166,13 @@ int pdk_pair_energy_grad(const float* x, const float* x_exists, const float* sig
                          const int32_t* rows, const uint8_t* in_rows, int64_t n_rows, float clash_k, float clash_scale,
                          float cutoff, float softcore, float* e_row, float* energy, float* grad, int64_t B, int64_t Na,
                          void* stream);
+/* `iters` projected-gradient steps x <- x - step * clamp(grad E(x), +-gmax) on the row atoms in ONE launch (one CTA per
+ * sample, the sample staged in shared memory; same arithmetic as pdk_pair_energy_grad + pdk_descent_update repeated).
+ * Replaces the `maxIters=mmff_iters` minimiser loop of get_next_step_pos (model.py:43).  rows / in_rows are required. */
+int pdk_pair_descend(const float* x, const float* x_exists, const float* sigma, const float* eps, const int32_t* partner,
+                     const float* partner_r0, const float* partner_k, int64_t E, const int32_t* rows, const uint8_t* in_rows,
+                     int64_t n_rows, float clash_k, float clash_scale, float cutoff, float softcore, int64_t iters, float step,
+                     float gmax, float* x_out, int64_t B, int64_t Na, void* stream);
 /* One projected-gradient step: x_out = x - step * clamp(grad, +-gmax) on the row atoms, copy elsewhere. */
 int pdk_descent_update(const float* x, const float* grad, const uint8_t* in_rows, float step, float gmax, float* x_out,
                        int64_t B, int64_t Na, void* stream);

@@ -160,6 +160,9 @@ def make_c1():
     assert all(torch.isfinite(t).all() for t in (a, ap, s, z))
     batch = {k: tensors[k] for k in HOT_KEYS}
     d = {f"batch_{k}": npy(v) for k, v in batch.items()}
+    # what the physics parameter source reads (physics.field_from_features): elements and token bonds
+    d["extra_ref_element"] = npy(tensors["ref_feat"][:, 4:132].argmax(-1) + 1)
+    d["extra_token_bonds"] = npy(tensors["token_bonds"])
     d.update(a=npy(a.half()), ap=npy(ap.half()), s=npy(s.half()), z=npy(z.half()), Nt=Nt, Na=Na,
              sd_checksum=checksum(torch.cat([v.flatten() for v in sd.values()])))
     dit = model.dit

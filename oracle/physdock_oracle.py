@@ -537,6 +537,54 @@ def rank_conformer_templates(x_pred_lig: Tensor, ref_mol_poses: Tensor, n_keep: 
     return torch.argsort(epsilon)[:n_keep]
 
 
+def rounds_bookkeeping(x_preds, is_ligand_atom: Tensor, ref_mol_poses: Optional[Tensor], accept_fn,
+                       num_augmentation_sample: int, max_samples: int, physics_correction: bool,
+                       mmff_gamma_0_factor_start: float):
+    """The per-system round loop of redocking.py:163-338 with the model call replaced by the recorded predictions
+    `x_preds` (one [B,Na,3] CPU tensor per executed round): accept/reject lists (:302-317), adaptive boundary (:318-322),
+    early stop (:323-324), conformer ranking for the next round's reference templates (:326-335), reject fill-in (:337-338).
+    Returns (per-round dicts, final accepted stack [<= max_samples, Na, 3], n_accepted, final factor)."""
+    from collections import deque
+    accept_samples, reject_samples = [], deque([], maxlen=max_samples)
+    ligand_templates, reference_templates = [], []
+    mmff_gamma_0_factor = mmff_gamma_0_factor_start
+    out = []
+    for recycle_id, x_pred in enumerate(x_preds):
+        assert recycle_id == 0 or physics_correction
+        n_templates = len(ligand_templates) + len(reference_templates) if recycle_id > 0 else 0
+        factor_used = mmff_gamma_0_factor
+        pass_flags = []
+        for x in x_pred:
+            pass_flag = bool(accept_fn(x)) if (physics_correction and accept_fn is not None) else True
+            pass_flags.append(pass_flag)
+            if pass_flag:
+                ligand_templates.append(x[is_ligand_atom])
+                accept_samples.append(x)
+            else:
+                reject_samples.append(x)
+        used_inds = None
+        stop = False
+        if physics_correction:
+            if any(pass_flags):
+                mmff_gamma_0_factor = mmff_gamma_0_factor * 1.15
+            else:
+                mmff_gamma_0_factor = max(mmff_gamma_0_factor * 0.7, 1)
+            if len(accept_samples) >= max_samples:
+                stop = True
+            else:
+                used_inds = rank_conformer_templates(x_pred[:, is_ligand_atom], ref_mol_poses,
+                                                     max_samples - len(ligand_templates))
+                reference_templates = [ref_mol_poses[i] for i in used_inds]
+        out.append(dict(recycle_id=recycle_id, factor=factor_used, pass_flags=pass_flags, n_templates=n_templates,
+                        used_inds=used_inds, stop=stop))
+        if stop:
+            break
+    n_accepted = len(accept_samples)
+    if len(accept_samples) < num_augmentation_sample:
+        accept_samples = accept_samples + [_ for _ in reject_samples]
+    return out, torch.stack(accept_samples[:max_samples], dim=0), n_accepted, mmff_gamma_0_factor
+
+
 def rmsd(a: Tensor, b: Tensor) -> Tensor:
     """Per-sample RMSD in Angstrom between two coordinate sets [B,N,3] (the parity metric)."""
     return ((a.double() - b.double()) ** 2).sum(-1).mean(-1).sqrt()

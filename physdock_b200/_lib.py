@@ -68,6 +68,7 @@ PROTOTYPES = {
     "pdk_pairwise_rmsd": (_int, [_vp, _vp, _i64, _i64, _vp]),
     "pdk_pair_energy_grad": (_int, [_vp] * 7 + [_i64, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _vp, _vp, _vp, _i64, _i64,
                                     _vp]),
+    "pdk_pair_descend": (_int, [_vp] * 7 + [_i64, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _i64, _f32, _f32, _vp, _i64, _i64, _vp]),
     "pdk_descent_update": (_int, [_vp, _vp, _vp, _f32, _f32, _vp, _i64, _i64, _vp]),
     "pdk_op_pair_bias": (_int, [_vp] * 5 + [_i64] * 4 + [_f32, _f32, _vp]),
     "pdk_op_time_embed": (_int, [_vp] * 6 + [_f32, _vp, _vp, _i64, _vp]),

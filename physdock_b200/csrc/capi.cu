@@ -452,6 +452,18 @@ int pdk_pair_energy_grad(const float* x, const float* x_exists, const float* sig
     return 0;
 }
 
+int pdk_pair_descend(const float* x, const float* x_exists, const float* sigma, const float* eps, const int32_t* partner,
+                     const float* partner_r0, const float* partner_k, int64_t E, const int32_t* rows, const uint8_t* in_rows,
+                     int64_t n_rows, float clash_k, float clash_scale, float cutoff, float softcore, int64_t iters, float step,
+                     float gmax, float* x_out, int64_t B, int64_t Na, void* stream) {
+    if (!x || !x_exists || !sigma || !eps || !rows || !in_rows || !x_out) return fail_msg("pdk_pair_descend", "null argument");
+    if (E > 0 && (!partner || !partner_r0 || !partner_k)) return fail_msg("pdk_pair_descend", "partner table missing");
+    const PairEnergyParams pp{clash_k, clash_scale, cutoff * cutoff, softcore};
+    PDK_TRY("pair_descend", launch_pair_descend(x, x_exists, sigma, eps, partner, partner_r0, partner_k, (int)E, rows, in_rows,
+                                                (int)n_rows, (int)iters, step, gmax, x_out, (int)B, (int)Na, pp, S(stream)));
+    return 0;
+}
+
 int pdk_descent_update(const float* x, const float* grad, const uint8_t* in_rows, float step, float gmax, float* x_out,
                        int64_t B, int64_t Na, void* stream) {
     if (!x || !grad || !x_out) return fail_msg("pdk_descent_update", "null argument");

@@ -135,6 +135,12 @@ cudaError_t launch_pair_energy_grad(const float* x, const float* exists, const f
                                     const int* partner, const float* p_r0, const float* p_k, int E, const int* rows,
                                     const unsigned char* in_rows, int n_rows, float* e_row, float* energy, float* grad,
                                     int B, int Na, const PairEnergyParams& pp, cudaStream_t st);
+// `iters` descent steps on the row atoms in one launch (rows / in_rows required); cudaErrorInvalidValue when the sample does
+// not fit one CTA's shared memory
+cudaError_t launch_pair_descend(const float* x, const float* exists, const float* sigma, const float* eps, const int* partner,
+                                const float* p_r0, const float* p_k, int E, const int* rows, const unsigned char* in_rows,
+                                int n_rows, int iters, float step, float gmax, float* x_out, int B, int Na,
+                                const PairEnergyParams& pp, cudaStream_t st);
 cudaError_t launch_descent_update(const float* x, const float* grad, const unsigned char* in_rows, float step, float gmax,
                                   float* x_out, int B, int Na, cudaStream_t st);
 

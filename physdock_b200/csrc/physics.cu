@@ -57,6 +57,68 @@ PDK_DEV PairTerm nonbonded_term(float d2, float d, float inv_d, float sig, float
     return t;
 }
 
+// Force (= dE/dx_i) and energy share of row atom i against the staged sample; the whole warp cooperates (lanes stride over
+// the partners j), every lane returns the warp totals.  Shared by the gradient kernel and the fused descent kernel, so both
+// produce the same bits.
+struct RowForce { float fx, fy, fz, en; };
+PDK_DEV RowForce row_force(int i, const float4* sx, const float* se, const unsigned char* sr, uint32_t* smask, int mask_words,
+                           const int* __restrict__ partner, const float* __restrict__ p_r0, const float* __restrict__ p_k, int E,
+                           int Na, const PairEnergyParams& pp) {
+    const int lane = threadIdx.x & 31;
+        // exclusion bitmask of row i: itself + its partner table
+    for (int w = lane; w < mask_words; w += 32) smask[w] = 0u;
+    __syncwarp();
+    if (lane == 0) smask[i >> 5] |= 1u << (i & 31);
+    __syncwarp();
+    for (int e = 0; e < E; ++e) {                            // serial: two partners may share a word
+        const int j = partner[(size_t)i * E + e];
+        if (lane == 0 && j >= 0) smask[j >> 5] |= 1u << (j & 31);
+    }
+    __syncwarp();
+    const float4 xi = sx[i];
+    const float sei = se[i];
+    float fx = 0.f, fy = 0.f, fz = 0.f, en = 0.f;
+    for (int j0 = 0; j0 < Na; j0 += 32) {
+        const int j = j0 + lane;
+        const uint32_t m = smask[j0 >> 5];                  // broadcast
+        if (j < Na && !((m >> lane) & 1u)) {
+            const float4 xj = sx[j];
+            const float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+            const float r2 = dx * dx + dy * dy + dz * dz;
+            const float sej = se[j];
+            const float epsij = sei * sej;
+            if (r2 < pp.cutoff2 && sej >= 0.f && sei >= 0.f) {
+                const float d2 = r2 + 1e-12f;
+                const float inv_d = rsqrtf(d2);
+                const float d = d2 * inv_d;
+                const PairTerm t = nonbonded_term(d2, d, inv_d, 0.5f * (xi.w + xj.w), epsij, pp);
+                const float w = sr[j] ? 0.5f : 1.0f;
+                en = fmaf(w, t.e, en);
+                const float g = t.dedd;                     // (dE/dd)/d; gradient weight is 1 for both kinds of pair
+                fx = fmaf(g, dx, fx); fy = fmaf(g, dy, fy); fz = fmaf(g, dz, fz);
+            }
+        }
+    }
+    // bonded / restraint terms of row i: lane e handles partner e
+    for (int e = lane; e < E; e += 32) {
+        const int j = partner[(size_t)i * E + e];
+        const float k = p_k[(size_t)i * E + e];
+        if (j >= 0 && k != 0.f && sei >= 0.f && se[j] >= 0.f) {
+            const float4 xj = sx[j];
+            const float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+            const float d = sqrtf(dx * dx + dy * dy + dz * dz + 1e-12f);
+            const float dev = d - p_r0[(size_t)i * E + e];
+            const float w = sr[j] ? 0.5f : 1.0f;
+            en = fmaf(w, k * dev * dev, en);
+            const float g = 2.0f * k * dev / d;
+            fx = fmaf(g, dx, fx); fy = fmaf(g, dy, fy); fz = fmaf(g, dz, fz);
+        }
+    }
+    RowForce out;
+    out.fx = warp_sum(fx); out.fy = warp_sum(fy); out.fz = warp_sum(fz); out.en = warp_sum(en);
+    return out;
+}
+
 template <int RPW>
 __global__ void __launch_bounds__(PHYS_THREADS)
 pair_energy_grad_kernel(const float* __restrict__ x, const float* __restrict__ exists, const float* __restrict__ sigma,
@@ -85,56 +147,8 @@ pair_energy_grad_kernel(const float* __restrict__ x, const float* __restrict__ e
         const int r = blockIdx.x * (8 * RPW) + rq * 8 + warp;
         if (r >= n_rows) break;                                  // warp-uniform
         const int i = rows ? rows[r] : r;
-        // exclusion bitmask of row i: itself + its partner table
-        for (int w = lane; w < mask_words; w += 32) smask[w] = 0u;
-        __syncwarp();
-        if (lane == 0) smask[i >> 5] |= 1u << (i & 31);
-        __syncwarp();
-        for (int e = 0; e < E; ++e) {                            // serial: two partners may share a word
-            const int j = partner[(size_t)i * E + e];
-            if (lane == 0 && j >= 0) smask[j >> 5] |= 1u << (j & 31);
-        }
-        __syncwarp();
-        const float4 xi = sx[i];
-        const float sei = se[i];
-        float fx = 0.f, fy = 0.f, fz = 0.f, en = 0.f;
-        for (int j0 = 0; j0 < Na; j0 += 32) {
-            const int j = j0 + lane;
-            const uint32_t m = smask[j0 >> 5];                  // broadcast
-            if (j < Na && !((m >> lane) & 1u)) {
-                const float4 xj = sx[j];
-                const float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
-                const float r2 = dx * dx + dy * dy + dz * dz;
-                const float sej = se[j];
-                const float epsij = sei * sej;
-                if (r2 < pp.cutoff2 && sej >= 0.f && sei >= 0.f) {
-                    const float d2 = r2 + 1e-12f;
-                    const float inv_d = rsqrtf(d2);
-                    const float d = d2 * inv_d;
-                    const PairTerm t = nonbonded_term(d2, d, inv_d, 0.5f * (xi.w + xj.w), epsij, pp);
-                    const float w = sr[j] ? 0.5f : 1.0f;
-                    en = fmaf(w, t.e, en);
-                    const float g = t.dedd;                     // (dE/dd)/d; gradient weight is 1 for both kinds of pair
-                    fx = fmaf(g, dx, fx); fy = fmaf(g, dy, fy); fz = fmaf(g, dz, fz);
-                }
-            }
-        }
-        // bonded / restraint terms of row i: lane e handles partner e
-        for (int e = lane; e < E; e += 32) {
-            const int j = partner[(size_t)i * E + e];
-            const float k = p_k[(size_t)i * E + e];
-            if (j >= 0 && k != 0.f && sei >= 0.f && se[j] >= 0.f) {
-                const float4 xj = sx[j];
-                const float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
-                const float d = sqrtf(dx * dx + dy * dy + dz * dz + 1e-12f);
-                const float dev = d - p_r0[(size_t)i * E + e];
-                const float w = sr[j] ? 0.5f : 1.0f;
-                en = fmaf(w, k * dev * dev, en);
-                const float g = 2.0f * k * dev / d;
-                fx = fmaf(g, dx, fx); fy = fmaf(g, dy, fy); fz = fmaf(g, dz, fz);
-            }
-        }
-        fx = warp_sum(fx); fy = warp_sum(fy); fz = warp_sum(fz); en = warp_sum(en);
+        const RowForce f = row_force(i, sx, se, sr, smask, mask_words, partner, p_r0, p_k, E, Na, pp);
+        const float fx = f.fx, fy = f.fy, fz = f.fz, en = f.en;
         if (lane == 0) {
             e_row[(size_t)b * n_rows + r] = en;
             float* g = grad + ((size_t)b * Na + i) * 3;
@@ -170,6 +184,58 @@ __global__ void __launch_bounds__(256) descent_update_kernel(const float* __rest
             v = fmaf(-step, g, v);
         }
         x_out[t] = v;
+    }
+}
+
+// `iters` projected-gradient steps x <- x - step * clamp(grad E(x), +-gmax) on the row atoms in ONE launch (the multi-launch
+// path is 2 launches per iteration).  One CTA per sample: only the rows move and every partner coordinate is already staged in
+// shared memory, so the iterations need nothing but CTA barriers.  Same per-row arithmetic as pair_energy_grad_kernel +
+// descent_update_kernel (row_force above), hence the same bits.
+constexpr int DESC_THREADS = 1024;
+__global__ void __launch_bounds__(DESC_THREADS)
+pair_descend_kernel(const float* __restrict__ x, const float* __restrict__ exists, const float* __restrict__ sigma,
+                    const float* __restrict__ eps, const int* __restrict__ partner, const float* __restrict__ p_r0,
+                    const float* __restrict__ p_k, int E, const int* __restrict__ rows, const unsigned char* __restrict__ in_rows,
+                    int n_rows, int iters, float step, float gmax, float* __restrict__ x_out, int Na, PairEnergyParams pp) {
+    extern __shared__ __align__(16) uint8_t smem_p[];
+    float4* sx = reinterpret_cast<float4*>(smem_p);
+    float* se = reinterpret_cast<float*>(sx + Na);
+    unsigned char* sr = reinterpret_cast<unsigned char*>(se + Na);
+    const int mask_words = (Na + 31) / 32;
+    uint32_t* smask_all = reinterpret_cast<uint32_t*>(sr + ((Na + 15) & ~15));
+    float* sg = reinterpret_cast<float*>(smask_all + (DESC_THREADS / 32) * mask_words);      // [n_rows][3]
+    uint32_t* smask = smask_all + (threadIdx.x >> 5) * mask_words;
+    const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    griddep_launch();
+    griddep_wait();
+    const float* xb = x + (size_t)b * Na * 3;
+    for (int j = threadIdx.x; j < Na; j += DESC_THREADS) {
+        const float ex = exists[j];
+        sx[j] = make_float4(xb[3 * j], xb[3 * j + 1], xb[3 * j + 2], sigma[j]);
+        se[j] = ex != 0.f ? sqrtf(fmaxf(eps[j], 0.f)) : -1.f;
+        sr[j] = in_rows[j];
+    }
+    __syncthreads();
+    for (int it = 0; it < iters; ++it) {
+        for (int r = warp; r < n_rows; r += DESC_THREADS / 32) {
+            const RowForce f = row_force(rows[r], sx, se, sr, smask, mask_words, partner, p_r0, p_k, E, Na, pp);
+            if (lane == 0) { sg[3 * r] = f.fx; sg[3 * r + 1] = f.fy; sg[3 * r + 2] = f.fz; }
+            __syncwarp();
+        }
+        __syncthreads();             // every row's gradient is taken at the same iterate
+        for (int r = threadIdx.x; r < n_rows; r += DESC_THREADS) {
+            float4 v = sx[rows[r]];
+            v.x = fmaf(-step, fminf(fmaxf(sg[3 * r], -gmax), gmax), v.x);
+            v.y = fmaf(-step, fminf(fmaxf(sg[3 * r + 1], -gmax), gmax), v.y);
+            v.z = fmaf(-step, fminf(fmaxf(sg[3 * r + 2], -gmax), gmax), v.z);
+            sx[rows[r]] = v;
+        }
+        __syncthreads();
+    }
+    float* ob = x_out + (size_t)b * Na * 3;
+    for (int j = threadIdx.x; j < Na; j += DESC_THREADS) {
+        const float4 v = sx[j];
+        ob[3 * j] = v.x; ob[3 * j + 1] = v.y; ob[3 * j + 2] = v.z;
     }
 }
 
@@ -219,6 +285,28 @@ cudaError_t launch_descent_update(const float* x, const float* grad, const unsig
     const size_t total = (size_t)B * Na * 3;
     const int blocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);      // <= 8 CTAs per SM
     PDK_LAUNCH_CHECK(launch_pdl(descent_update_kernel, dim3(blocks), dim3(256), 0, st, x, grad, in_rows, step, gmax, x_out, B, Na));
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pair_descend(const float* x, const float* exists, const float* sigma, const float* eps, const int* partner,
+                                const float* p_r0, const float* p_k, int E, const int* rows, const unsigned char* in_rows,
+                                int n_rows, int iters, float step, float gmax, float* x_out, int B, int Na,
+                                const PairEnergyParams& pp, cudaStream_t st) {
+    if (B <= 0 || Na <= 0 || n_rows <= 0 || E < 0 || iters < 0 || rows == nullptr || in_rows == nullptr) return cudaErrorInvalidValue;
+    const int mask_words = (Na + 31) / 32;
+    const size_t smem = (size_t)Na * 16 + (size_t)Na * 4 + (size_t)((Na + 15) & ~15) + (size_t)(DESC_THREADS / 32) * mask_words * 4 +
+                        (size_t)n_rows * 12;
+    if (smem > 227 * 1024) return cudaErrorInvalidValue;       // the caller falls back to the multi-launch path
+    static size_t configured[kMaxDevices] = {};
+    int dev = 0;
+    cudaError_t e = current_device(&dev);
+    if (e != cudaSuccess) return e;
+    if (smem > 48 * 1024 && smem > configured[dev]) {
+        if ((e = cudaFuncSetAttribute(pair_descend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        configured[dev] = smem;
+    }
+    PDK_LAUNCH_CHECK(launch_pdl(pair_descend_kernel, dim3(B), dim3(DESC_THREADS), smem, st, x, exists, sigma, eps, partner, p_r0, p_k, E,
+                                rows, in_rows, n_rows, iters, step, gmax, x_out, Na, pp));
     return cudaGetLastError();
 }
 

@@ -104,6 +104,27 @@ def weighted_rigid_align(x_den, x_exists, x_gt, weights, out=None):
     return out
 
 
+def _rdkit_conformers(ref_mol, num_confs: int = 512):
+    """The conformer pool of model.py:188-203 (RDKit EmbedMultipleConfs, enforceChirality=True).  Third-party, un-vendored:
+    only reachable where rdkit is importable."""
+    try:
+        import copy
+        from rdkit.Chem import AllChem
+    except Exception as e:  # pragma: no cover - rdkit is absent from this image
+        raise _lib.PdkError("use_ref_mol_poses=True without ref_mol_poses needs RDKit EmbedMultipleConfs (model.py:185-203): "
+                            "pass ref_mol_poses, or conformer_fn=... returning [C, n_lig, 3]") from e
+    mol = copy.deepcopy(ref_mol)                                                   # pragma: no cover
+    cids = AllChem.EmbedMultipleConfs(mol, numConfs=num_confs, enforceChirality=True)   # pragma: no cover
+    n = mol.GetNumAtoms()                                                          # pragma: no cover
+    out = torch.zeros(num_confs, n, 3)                                             # pragma: no cover
+    for i, cid in enumerate(cids):                                                 # pragma: no cover
+        conf = mol.GetConformer(cid)
+        for j in range(n):
+            pos = conf.GetAtomPosition(j)
+            out[i, j, 0], out[i, j, 1], out[i, j, 2] = pos.x, pos.y, pos.z
+    return out                                                                     # pragma: no cover
+
+
 def _rdkit_mmff(ref_mol, mmff_iters):
     """get_next_step_pos (model.py:26-52): RDKit MMFF94 on the ligand alone, on the CPU, per sample.
     Third-party, un-vendored (rdkit==2024.3.3, enviroment.yaml:33): parity unpinned, see DESIGN.md."""
@@ -146,7 +167,7 @@ class DiffusionSampler:
                  mmff_gamma_0_factor: float = 1.0, mmff_iters: int = 5, align_ref_pos: bool = True,
                  karras_noise_schedule_power: float = 7, rng=None, mmff_fn: Optional[Callable] = None,
                  use_cuda_graph: bool = True, physics_field=None, physics_step: float = 0.002,
-                 physics_gmax: float = 50.0):
+                 physics_gmax: float = 50.0, conformer_fn: Optional[Callable] = None):
         dev = batch["x_gt"].device
         self.use_cuda_graph = use_cuda_graph
         if dev.type != "cuda":
@@ -164,8 +185,9 @@ class DiffusionSampler:
         self.batch_ref_pos = batch["ref_pos"].to(dev).float()[None].repeat([self.B, 1, 1]).contiguous()
         self.ref_mol_poses, self.ref_dist = None, None
         if ref_mol_poses is None and use_ref_mol_poses:
-            raise _lib.PdkError("use_ref_mol_poses=True needs RDKit EmbedMultipleConfs (model.py:185-203); "
-                                "generate conformers on the host and pass ref_mol_poses instead")
+            # model.py:185-203: 512 RDKit conformers; `conformer_fn() -> [C, n_lig, 3]` is the host hook for it (like mmff_fn)
+            ref_mol_poses = conformer_fn() if conformer_fn is not None else _rdkit_conformers(ref_mol, 512)
+            ref_mol_poses = ref_mol_poses[:, :int(self.is_ligand_atom.sum())]
         if ref_mol_poses is not None:
             self.ref_mol_poses = ref_mol_poses.to(dev).float().contiguous()
             if self.ref_mol_poses.shape[1] != self.lig_idx.numel():     # the reference swallows this (try/except)
@@ -339,10 +361,12 @@ def sample_diffusion(dit: B200DiT, batch: Dict[str, torch.Tensor], a, ap, s, z, 
                      align_ref_pos: bool = True, karras_noise_schedule_power: float = 7, rng=None,
                      mmff_fn: Optional[Callable] = None, trace: Optional[List[dict]] = None,
                      teacher: Optional[List[dict]] = None, max_steps: Optional[int] = None, physics_field=None,
-                     physics_step: float = 0.002, physics_gmax: float = 50.0) -> torch.Tensor:
+                     physics_step: float = 0.002, physics_gmax: float = 50.0,
+                     conformer_fn: Optional[Callable] = None) -> torch.Tensor:
     """`PhysDock.sample_diffusion` (model.py:157-282) given the trunk outputs (a, ap, s, z).
 
-    Extra hooks (not in the reference): `rng` (object with rand/normal), `mmff_fn`, `physics_field` (a
+    Extra hooks (not in the reference): `rng` (object with rand/normal), `mmff_fn`, `conformer_fn` (host hooks for the two
+    RDKit calls, MMFFOptimizeMolecule and EmbedMultipleConfs), `physics_field` (a
     physics.PairEnergyField: GPU replacement of the MMFF step), `trace` (list that
     receives per-step tensors), `teacher` (per-step dicts with an `x_hat` to feed the denoiser instead of the
     free-running one: teacher-forced parity).
@@ -353,7 +377,8 @@ def sample_diffusion(dit: B200DiT, batch: Dict[str, torch.Tensor], a, ap, s, z, 
                            use_ref_mol_poses=use_ref_mol_poses, mmff_gamma_0_factor=mmff_gamma_0_factor,
                            mmff_iters=mmff_iters, align_ref_pos=align_ref_pos,
                            karras_noise_schedule_power=karras_noise_schedule_power, rng=rng, mmff_fn=mmff_fn,
-                           physics_field=physics_field, physics_step=physics_step, physics_gmax=physics_gmax)
+                           physics_field=physics_field, physics_step=physics_step, physics_gmax=physics_gmax,
+                           conformer_fn=conformer_fn)
     x = smp.begin()
     for i in range(steps):
         if max_steps is not None and i >= max_steps:

@@ -83,6 +83,7 @@ def c1_fixture():
     if "c1" not in _cache:
         g = load_npz("c1_5sd5.npz")
         batch = {k[len("batch_"):]: T(g[k]) for k in g if k.startswith("batch_")}
+        batch["token_bonds"] = T(g["extra_token_bonds"])
         cond = {k: T(g[k]).float() for k in ("a", "ap", "s", "z")}
         _cache["c1"] = (g, batch, cond)
     return _cache["c1"]

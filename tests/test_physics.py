@@ -117,3 +117,68 @@ def test_descend_vs_oracle_and_idempotent_inputs():
     assert bool((e1 < e0).all())
     again = fld.descend(xd, iters=5, step=0.002, gmax=50.0)       # deterministic: bit-identical on a second run
     assert torch.equal(again, got)
+
+
+# ------------------------------------------------------------------------------------------- parameter sources (row f4)
+def test_parameters_from_reference_features_on_real_ligand():
+    """physics.parameters_from_features on the real 5SD5/HWI features (tests/golden/c1_5sd5.npz): UFF (sigma, eps) by element,
+    bonds from token_bonds with lengths from the reference conformer, 1-3 restraints, ligand rows."""
+    from physdock_b200.physics import parameters_from_features, UFF_X_D
+    from tests.helpers import c1_fixture, T
+    g, batch, _ = c1_fixture()
+    elements = T(g["extra_ref_element"])
+    f = parameters_from_features(batch, elements=elements)
+    Na = int(g["Na"])
+    assert f["rows"].numel() == 29 and f["sigma"].shape == (Na,) and f["eps"].shape == (Na,)
+    lig = f["rows"].long()
+    assert set(elements[lig].tolist()) <= set(UFF_X_D), "every ligand element has a UFF entry"
+    assert float(f["sigma"].min()) > 2.0 and float(f["sigma"].max()) < 4.2 and float(f["eps"].min()) > 0
+    bonds = f["bonds"]
+    assert len(bonds) >= 28, "a connected 29-atom ligand has at least 28 bonds"
+    is_row = torch.zeros(Na, dtype=torch.bool)
+    is_row[lig] = True
+    assert all(is_row[i] and is_row[j] for i, j in bonds)
+    partner, r0, k = f["partner"], f["partner_r0"], f["partner_k"]
+    for i in range(Na):                                   # symmetric table; covalent bond lengths; receptor atoms carry no partners
+        for e in range(partner.shape[1]):
+            j = int(partner[i, e])
+            if j < 0:
+                continue
+            assert is_row[i] and is_row[j]
+            back = (partner[j] == i).nonzero().flatten()
+            assert back.numel() == 1 and float(r0[j, back[0]]) == float(r0[i, e]) and float(k[j, back[0]]) == float(k[i, e])
+            if float(k[i, e]) == 300.0:
+                assert 1.0 < float(r0[i, e]) < 2.0, (i, j, float(r0[i, e]))
+            else:
+                assert 1.8 < float(r0[i, e]) < 3.2, (i, j, float(r0[i, e]))
+    # the reference conformer is (by construction) a minimum of the bonded terms
+    e_bond = O.pair_energy(batch["ref_pos"][None], batch["a_mask"], f["sigma"], f["eps"], partner, r0, k, f["rows"])
+    assert torch.isfinite(e_bond).all()
+
+
+@pytest.mark.gpu
+def test_fused_descend_equals_multi_launch_and_lowers_real_ligand_energy():
+    """pdk_pair_descend (one launch for all iterations) == repeated pdk_pair_energy_grad + pdk_descent_update, bit for bit, on
+    the synthetic field and on the real 5SD5 ligand with feature-derived parameters; the energy goes down."""
+    from physdock_b200.physics import PairEnergyField, field_from_features
+    from tests.helpers import c1_fixture, T
+    f, x = _case(2048, 32, 16, seed=3, missing=True)
+    fld = PairEnergyField(f["x_exists"].cuda(), f["sigma"], f["eps"], f["partner"], f["partner_r0"], f["partner_k"], rows=f["rows"])
+    assert fld.launches_per_descend(5) == 1
+    a = fld.descend(x.cuda(), iters=5, step=0.002, gmax=50.0)
+    b = fld.descend(x.cuda(), iters=5, step=0.002, gmax=50.0, fused=False)
+    assert torch.equal(a, b), float((a - b).abs().max())
+    g, batch, _ = c1_fixture()
+    d = {k: v.cuda() for k, v in batch.items()}
+    fld = field_from_features(d, elements=T(g["extra_ref_element"]))
+    gen = torch.Generator().manual_seed(1)
+    x0 = (batch["x_gt"][None] + 0.15 * torch.randn(4, int(g["Na"]), 3, generator=gen)).cuda()
+    e0, _ = fld.energy_grad(x0)
+    e0 = e0.clone()
+    x1 = fld.descend(x0, iters=20, step=0.001, gmax=50.0)
+    assert torch.equal(x1, fld.descend(x0, iters=20, step=0.001, gmax=50.0, fused=False))
+    e1, _ = fld.energy_grad(x1)
+    assert bool((e1 < e0).all()), (e0.tolist(), e1.tolist())
+    notlig = torch.ones(int(g["Na"]), dtype=torch.bool)
+    notlig[fld.rows.long().cpu()] = False
+    assert torch.equal(x1[:, notlig.cuda()], x0[:, notlig.cuda()]), "only the ligand moves"
