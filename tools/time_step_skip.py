@@ -6,9 +6,9 @@ import sys, os, subprocess, json
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GROUPS = [("full step", ""), ("attention (atom + token)", "attention"), ("QKV GEMMs", "gemm(qkv)"), ("out-proj GEMMs", "gemm(out)"),
           ("token SwiGLU GEMM", "gemm(w13)"), ("token w2 GEMM", "gemm(w2)"), ("atom fused transition", "transition"),
-          ("AdaLN kernels", "adaln"), ("conditioning (time embedding + modulation GEMM)", "time_embed,gemm(mod)"),
-          ("glue (precond, down/upscale, pooling, output)", "precond,segment_mean,gather_add,denoise_out,split,gemm(down),gemm(up)"),
-          ("coordinate kernels (augment, Euler)", "centre_augment,euler")]
+          ("AdaLN kernels", "adaln"),
+          ("glue (precond, down/upscale, pooling, output + fused Euler)", "precond,segment_mean,gather_add,denoise_out,split,gemm(down),gemm(up)"),
+          ("coordinate kernel (centre + augment + noise)", "centre_augment")]
 if len(sys.argv) > 1 and sys.argv[1] == "child":
     import torch
     sys.path.insert(0, ROOT)
