@@ -513,6 +513,11 @@ def get_representatives(distance_matrix, num_clusters: int = 5):
 def rank_poses(pred, num_clusters: int = 5):
     """redocking.py:412-423."""
     dist = pairwise_pose_rmsd(pred)
+    return rank_from_distance_matrix(dist, num_clusters), dist
+
+
+def rank_from_distance_matrix(dist, num_clusters: int = 5):
+    """redocking.py:412-423 given the pose-RMSD matrix of redocking.py:391."""
     if len(dist) > num_clusters:
         ids = get_representatives(dist, num_clusters)
         ids_1 = get_representatives(dist, 1)[0]
@@ -523,7 +528,7 @@ def rank_poses(pred, num_clusters: int = 5):
             ids = [ids_1] + ids[:4]
     else:
         ids = list(range(len(dist)))
-    return ids, dist
+    return ids
 
 
 def rank_conformer_templates(x_pred_lig: Tensor, ref_mol_poses: Tensor, n_keep: int) -> Tensor:

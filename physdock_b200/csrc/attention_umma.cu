@@ -295,16 +295,25 @@ attention_umma_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_const
                 float mx = -INFINITY;
                 const uint32_t bt = sm + OFF_BIAS + (j & 1) * BIAS_TILE + bias_row;
                 mbar_wait(smem_u32(&bars.bias_full[j & 1]), ((uint32_t)j >> 1) & 1u);
+#ifdef PDK_ATTN_LD2          // A/B variant (tools/gemm_variants.sh ATTN_LD2): both halves of S in flight with one wait
+                uint32_t r[64];
+                tmem_ld32(ts, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
+                tmem_ld32(ts + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
+                tmem_ld_wait();
+#endif
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
-                    uint32_t r[32];
-                    tmem_ld32(ts + half * 32, r);
+#ifndef PDK_ATTN_LD2
+                    uint32_t rh[32];
+                    tmem_ld32(ts + half * 32, rh);
                     tmem_ld_wait();
+                    const uint32_t* r = rh - 32 * half;      // same indexing as the two-halves-in-flight variant
+#endif
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
                         const float4 b4 = lds128(bt + half * BIAS_HALF + (((uint32_t)c ^ sw) << 4));
-                        s2[16 * half + 2 * c] = add2(pack2(__uint_as_float(r[4 * c]), __uint_as_float(r[4 * c + 1])), pack2(b4.x, b4.y));
-                        s2[16 * half + 2 * c + 1] = add2(pack2(__uint_as_float(r[4 * c + 2]), __uint_as_float(r[4 * c + 3])), pack2(b4.z, b4.w));
+                        s2[16 * half + 2 * c] = add2(pack2(__uint_as_float(r[32 * half + 4 * c]), __uint_as_float(r[32 * half + 4 * c + 1])), pack2(b4.x, b4.y));
+                        s2[16 * half + 2 * c + 1] = add2(pack2(__uint_as_float(r[32 * half + 4 * c + 2]), __uint_as_float(r[32 * half + 4 * c + 3])), pack2(b4.z, b4.w));
                         float a0, a1, a2, a3;
                         unpack2(s2[16 * half + 2 * c], a0, a1);
                         unpack2(s2[16 * half + 2 * c + 1], a2, a3);

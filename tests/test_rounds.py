@@ -82,6 +82,9 @@ def test_run_rounds_matches_oracle_bookkeeping(physics):
     r = float(O.rmsd(res.aligned.cpu(), want_aligned).max())
     log_value(f"run_rounds(physics={physics}) aligned poses rmsd", r)
     assert r < 1e-3
-    ids, dist = O.rank_poses(res.aligned.cpu()[:, lig].numpy())      # same poses: only the RMSD kernel vs numpy differs
-    assert res.ranking_ids == ids
-    assert float((res.rmsd_matrix.cpu() - torch.from_numpy(dist)).abs().max()) < 1e-3
+    # the pose-RMSD matrix is the GPU part (vs the reference's numpy formula on the same poses); KMeans on 8 unclustered
+    # poses flips on last-bit differences of its input, so the host-side ranking rules are checked on the SAME matrix
+    dist_gpu = res.rmsd_matrix.cpu().numpy()
+    dist = O.pairwise_pose_rmsd(res.aligned.cpu()[:, lig].numpy())
+    assert float(abs(dist_gpu - dist).max()) < 1e-6
+    assert res.ranking_ids == O.rank_from_distance_matrix(dist_gpu)

@@ -108,3 +108,62 @@ def test_two_rank_screening_covers_library_in_order():
     for i, x in enumerate(out):
         g = torch.Generator().manual_seed(1000 + i)
         assert torch.equal(x, torch.randn(8, 20 + i, 3, generator=g))
+
+
+class _FakeModel:
+    """Stand-in for PhysDockB200 on CPU: trunk = identity on a feature, sampler = deterministic function of it."""
+
+    class _Dit(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.zeros(1))
+
+    def __init__(self):
+        self.dit = self._Dit()
+        self.trunk_calls = []
+
+    def diffusion_conditioning(self, batch):
+        self.trunk_calls.append(int(batch["lig"]))
+        return (batch["feat"] * 2,)
+
+    def sample_diffusion(self, batch, num_sample, steps, karras_noise_schedule_power, conditioning, **kw):
+        return conditioning[0][None].repeat(num_sample, 1, 1) + steps
+
+
+def _screen_ligands_worker(rank, ws, port, q):
+    from physdock_b200.screen import screen_ligands
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=ws)
+    model = _FakeModel()
+
+    def featurise(i):
+        if i == 3:
+            return None                       # featurisation failure: skipped, like screening.py:115-118
+        return {"feat": torch.full((4 + i, 3), float(i)), "lig": torch.tensor(i)}
+
+    for overlap in (True, False):
+        model.trunk_calls.clear()
+        out = screen_ligands(model, list(range(7)), featurise, num_sample=8, steps=40, overlap=overlap)
+        assert model.trunk_calls == [i for i in range(rank, 7, ws) if i != 3]
+        assert out[3] is None
+        for i, x in enumerate(out):
+            if i != 3:
+                assert x.shape == (8, 4 + i, 3) and bool((x == 2 * i + 40).all())
+    if rank == 0:
+        q.put("ok")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_screen_ligands_overlap_equals_serial():
+    """physdock_b200.screen.screen_ligands (BASELINE.json configs[3]): round-robin ligand shards, prefetch pipeline == serial."""
+    ws, port = 2, 29575
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_screen_ligands_worker, args=(r, ws, port, q)) for r in range(ws)]
+    for p in procs:
+        p.start()
+    assert q.get(timeout=120) == "ok"
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
