@@ -295,20 +295,14 @@ attention_umma_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_const
                 float mx = -INFINITY;
                 const uint32_t bt = sm + OFF_BIAS + (j & 1) * BIAS_TILE + bias_row;
                 mbar_wait(smem_u32(&bars.bias_full[j & 1]), ((uint32_t)j >> 1) & 1u);
-#ifdef PDK_ATTN_LD2          // A/B variant (tools/gemm_variants.sh ATTN_LD2): both halves of S in flight with one wait
+                // both 32-column halves of S in flight with ONE wait (two ld + wait pairs exposed the TMEM read latency twice per
+                // unit: atom attention 127.1 -> 125.2 us, token 13.3 -> 12.7 us, and the register allocator no longer spills)
                 uint32_t r[64];
                 tmem_ld32(ts, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
                 tmem_ld32(ts + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
                 tmem_ld_wait();
-#endif
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
-#ifndef PDK_ATTN_LD2
-                    uint32_t rh[32];
-                    tmem_ld32(ts + half * 32, rh);
-                    tmem_ld_wait();
-                    const uint32_t* r = rh - 32 * half;      // same indexing as the two-halves-in-flight variant
-#endif
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
                         const float4 b4 = lds128(bt + half * BIAS_HALF + (((uint32_t)c ^ sw) << 4));

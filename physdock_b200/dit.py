@@ -270,7 +270,8 @@ class B200DiT(nn.Module):
     def _complex_signature(batch, a, ap, s, z):
         ts = (a, ap, s, z, batch["ap_mask"], batch["z_mask"], batch["token_id_to_chunk_sizes"],
               batch["atom_id_to_token_id"])
-        return tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in ts)
+        # inference-mode tensors (a trunk run under torch.inference_mode) carry no version counter: they are immutable
+        return tuple((t.data_ptr(), -1 if t.is_inference() else t._version, tuple(t.shape)) for t in ts)
 
     def _ensure_workspace(self, B: int, dev) -> torch.Tensor:
         lib = _lib.load()
@@ -324,7 +325,9 @@ class B200DiT(nn.Module):
             if len(self._graphs) > 16:
                 self._graphs.clear()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            # thread_local: another host thread may be driving its own streams meanwhile (pipeline.prefetch_complexes runs the
+            # next complex's trunk on a side stream); only this thread's calls are part of / restricted by the capture
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
                 enqueue()
             self._graphs[key] = g
         g.replay()
