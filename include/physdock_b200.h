@@ -189,6 +189,14 @@ int pdk_op_mod_gemv(const float* tsilu, const float* wmod, const float* bmod, fl
                     int64_t n_mod, void* stream);
 int pdk_op_adaln(const float* x, const float* mod, int64_t mod_stride, int64_t mod_off, void* xh, void* xl,
                  int64_t B, int64_t S_pad, int64_t c, float eps, void* stream);
+/* the first AdaLN of the atom encoder / decoder also produces its input row: precond (transformers.py:222) resp. the
+ * gather-add of upscale (transformers.py:214-216); same arithmetic as pdk_op_precond / pdk_op_gather_add + pdk_op_adaln */
+int pdk_op_precond_adaln(const float* x_hat, const float* coef, const float* a, const float* wx, const float* bx, float* ba,
+                         const float* mod, int64_t mod_stride, int64_t mod_off, void* xh, void* xl, int64_t B, int64_t Na,
+                         int64_t S_pad, int64_t c_a, float eps, void* stream);
+int pdk_op_upscale_adaln(float* ba, const float* up, const int32_t* atom2tok, const float* mod, int64_t mod_stride,
+                         int64_t mod_off, void* xh, void* xl, int64_t B, int64_t Na, int64_t Sa_pad, int64_t St_pad,
+                         int64_t c_a, float eps, void* stream);
 int pdk_op_split(const float* x, void* xh, void* xl, int64_t n, void* stream);
 int pdk_op_gemm_store(const void* Ah, const void* Al, int64_t lda, const void* Wh, const void* Wl, int64_t ldw,
                       int64_t M, int64_t N, int64_t K, const float* bias, int act_silu, float* out, int64_t ldo,

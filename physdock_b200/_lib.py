@@ -74,6 +74,8 @@ PROTOTYPES = {
     "pdk_op_time_embed": (_int, [_vp] * 6 + [_f32, _vp, _vp, _i64, _vp]),
     "pdk_op_mod_gemv": (_int, [_vp] * 4 + [_i64, _i64, _vp]),
     "pdk_op_adaln": (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _i64, _i64, _i64, _f32, _vp]),
+    "pdk_op_precond_adaln": (_int, [_vp] * 7 + [_i64, _i64, _vp, _vp, _i64, _i64, _i64, _i64, _f32, _vp]),
+    "pdk_op_upscale_adaln": (_int, [_vp] * 4 + [_i64, _i64, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _f32, _vp]),
     "pdk_op_split": (_int, [_vp, _vp, _vp, _i64, _vp]),
     "pdk_op_gemm_store": (_int, [_vp, _vp, _i64, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _int, _vp, _i64, _vp]),
     "pdk_op_gemm_gate_resid": (_int, [_vp, _vp, _i64, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _i64, _i64,

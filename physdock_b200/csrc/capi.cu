@@ -130,13 +130,15 @@ inline bool fused_transition_enabled() {
 // One DiTBlock (transformers.py:155-159): x += Attn(x); x += Transition(x).
 // `mod` = modulation rows (all AdaLN-Zero layers side by side), `nmod` = stride between the rows of consecutive samples
 // in floats (0: one row shared by every sample, the sampler's case: all samples of a step have the same noise level).
+// first_adaln_done: the caller already produced x and its attention-AdaLN planes (launch_precond_adaln / launch_upscale_adaln).
 int run_block(const pdk_dit& h, const pdk_block_weights& bw, const Workspace& ws, const float* mod, int nmod, float* x,
-              int64_t B, int64_t Sp, int c, int hidden, const float* bias, cudaStream_t st) {
+              int64_t B, int64_t Sp, int c, int hidden, const float* bias, cudaStream_t st, bool first_adaln_done = false) {
     const int M = (int)(B * Sp);
     const int Hh = c / kHeadDim;
     const float eps = (float)h.d.eps;
     // --- attention (attentions.py:240-265)
-    PDK_TRY("adaln(attn)", launch_adaln(x, mod, nmod, (int)bw.mod_attn_off, ws.xh, ws.xl, (int)B, (int)Sp, c, eps, st));
+    if (!first_adaln_done)
+        PDK_TRY("adaln(attn)", launch_adaln(x, mod, nmod, (int)bw.mod_attn_off, ws.xh, ws.xl, (int)B, (int)Sp, c, eps, st));
     GemmArgs g{};
     g.Ah = ws.xh; g.Al = ws.xl; g.lda = c;
     g.Wh = H(bw.wqkv_h); g.Wl = H(bw.wqkv_l); g.ldw = c;
@@ -264,9 +266,10 @@ int pdk_dit_prepare_complex(pdk_dit* h, const float* a, const float* ap, const f
 
 int64_t pdk_dit_launches_per_denoise(const pdk_dit* h) {
     if (!h) return 0;
-    // time_embed, mod, precond | blocks | split, gemm(down), segmean | split, gemm(up), gather | denoise_out
+    // time_embed, mod | blocks (precond and the upscale gather-add ride in the first AdaLN of their atom stack) |
+    // split, gemm(down), segmean | split, gemm(up) | denoise_out
     const int64_t per_atom_block = fused_transition_enabled() ? kLaunchesPerFusedBlock : kLaunchesPerBlock;
-    return 3 + per_atom_block * 2 * h->d.n_atom_blocks + kLaunchesPerBlock * h->d.n_token_blocks + 3 + 3 + 1;
+    return 2 + per_atom_block * 2 * h->d.n_atom_blocks + kLaunchesPerBlock * h->d.n_token_blocks + 3 + 2 + 1;
 }
 // pdk_dit_denoise_cond: the two conditioning launches are not part of the step
 int64_t pdk_dit_launches_per_denoise_cond(const pdk_dit* h) { return h ? pdk_dit_launches_per_denoise(h) - 2 : 0; }
@@ -297,12 +300,17 @@ static int run_denoise(pdk_dit* h, const float* x_hat, const float* mod, int mod
     const int ca = (int)d.c_a, cs = (int)d.c_s;
     const int Ha = h->H_a(), Hs = h->H_s();
     const int nA = (int)d.n_atom_blocks, nT = (int)d.n_token_blocks;
-    PDK_TRY("precond", launch_precond(x_hat, coef, coef_stride, h->a, h->w.wx, h->w.bx, ws.ba, (int)B, (int)h->Na, (int)Sa, ca, st));
+    // precond (transformers.py:218-226) fused with the first AdaLN of the atom encoder: ba is produced, stored and normalised
+    // in one pass
+    PDK_TRY("precond+adaln", launch_precond_adaln(x_hat, coef, coef_stride, h->a, h->w.wx, h->w.bx, ws.ba, mod, mod_stride,
+                                                  (int)h->blocks[0].mod_attn_off, ws.xh, ws.xl, (int)B, (int)h->Na, (int)Sa, ca,
+                                                  (float)d.eps, st));
 
     // atom encoder (transformers.py:252)
     const size_t plane_a = (size_t)Ha * Sa * Sa, plane_t = (size_t)Hs * St * St;
     for (int l = 0; l < nA; ++l) {
-        int rc = run_block(*h, h->blocks[l], ws, mod, mod_stride, ws.ba, B, Sa, ca, (int)d.hidden_a, h->bias_atom + l * plane_a, st);
+        int rc = run_block(*h, h->blocks[l], ws, mod, mod_stride, ws.ba, B, Sa, ca, (int)d.hidden_a, h->bias_atom + l * plane_a, st,
+                           l == 0);
         if (rc) return rc;
     }
     // downscale (transformers.py:205-212)
@@ -331,11 +339,13 @@ static int run_denoise(pdk_dit* h, const float* x_hat, const float* mod, int mod
         g.bias = h->w.bup; g.out = ws.up; g.ldo = ca;
         PDK_TRY("gemm(up)", launch_gemm(EPI_STORE, g, st));
     }
-    PDK_TRY("gather_add", launch_gather_add(ws.ba, ws.up, h->atom2tok, (int)B, (int)h->Na, (int)Sa, (int)St, ca, st));
+    // ... the gather-add ba += up[atom_id_to_token_id] runs inside the first AdaLN of the atom decoder
+    PDK_TRY("upscale+adaln", launch_upscale_adaln(ws.ba, ws.up, h->atom2tok, mod, mod_stride, (int)h->blocks[nA + nT].mod_attn_off,
+                                                  ws.xh, ws.xl, (int)B, (int)h->Na, (int)Sa, (int)St, ca, (float)d.eps, st));
     // atom decoder (transformers.py:259)
     for (int l = 0; l < nA; ++l) {
         int rc = run_block(*h, h->blocks[nA + nT + l], ws, mod, mod_stride, ws.ba, B, Sa, ca, (int)d.hidden_a,
-                           h->bias_atom + (size_t)(nA + l) * plane_a, st);
+                           h->bias_atom + (size_t)(nA + l) * plane_a, st, l == 0);
         if (rc) return rc;
     }
     // denoise (transformers.py:228-233) [+ the physics-free Euler update, model.py:263-264,278-281]
@@ -497,6 +507,20 @@ int pdk_op_mod_gemv(const float* tsilu, const float* wmod, const float* bmod, fl
 int pdk_op_adaln(const float* x, const float* mod, int64_t mod_stride, int64_t mod_off, void* xh, void* xl, int64_t B,
                  int64_t S_pad, int64_t c, float eps, void* stream) {
     PDK_TRY("adaln", launch_adaln(x, mod, (int)mod_stride, (int)mod_off, H(xh), H(xl), (int)B, (int)S_pad, (int)c, eps, S(stream)));
+    return 0;
+}
+int pdk_op_precond_adaln(const float* x_hat, const float* coef, const float* a, const float* wx, const float* bx, float* ba,
+                         const float* mod, int64_t mod_stride, int64_t mod_off, void* xh, void* xl, int64_t B, int64_t Na,
+                         int64_t S_pad, int64_t c_a, float eps, void* stream) {
+    PDK_TRY("precond+adaln", launch_precond_adaln(x_hat, coef, 4, a, wx, bx, ba, mod, (int)mod_stride, (int)mod_off, H(xh), H(xl),
+                                                  (int)B, (int)Na, (int)S_pad, (int)c_a, eps, S(stream)));
+    return 0;
+}
+int pdk_op_upscale_adaln(float* ba, const float* up, const int32_t* atom2tok, const float* mod, int64_t mod_stride,
+                         int64_t mod_off, void* xh, void* xl, int64_t B, int64_t Na, int64_t Sa_pad, int64_t St_pad,
+                         int64_t c_a, float eps, void* stream) {
+    PDK_TRY("upscale+adaln", launch_upscale_adaln(ba, up, atom2tok, mod, (int)mod_stride, (int)mod_off, H(xh), H(xl), (int)B,
+                                                  (int)Na, (int)Sa_pad, (int)St_pad, (int)c_a, eps, S(stream)));
     return 0;
 }
 int pdk_op_split(const float* x, void* xh, void* xl, int64_t n, void* stream) {

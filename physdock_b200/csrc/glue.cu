@@ -115,24 +115,64 @@ __global__ void __launch_bounds__(256) mod_gemv_kernel(const float* __restrict__
 // ------------------------------------------------------------------------------------------------
 // AdaLN-Zero modulate: planes = split( LN_noaffine(x) * (1 + scale) + shift )   (adaptive_layer_norm_zero.py:20)
 // Warp per row; C/32 values per lane held in registers (C = 128 or 512).
-template <int C>
-__global__ void __launch_bounds__(256) adaln_kernel(const float* __restrict__ x, const float* __restrict__ mod,
+// The first AdaLN of each atom stack also PRODUCES its input row (SRC != 0, C = 128), which removes one launch and one
+// 16.8 MB read per stack:
+//   SRC_PRECOND  x = Linear_{3->c_a}(x_hat * c_in) + a, pad rows 0        (AF3DiT.precond, transformers.py:222)
+//   SRC_UPSCALE  x += up[b, atom_id_to_token_id[s], :] for s < Na          (AF3DiT.upscale, transformers.py:214-216)
+// with the same arithmetic as the stand-alone precond / gather_add kernels (bit-identical); the row is stored back to x.
+enum { SRC_X = 0, SRC_PRECOND = 1, SRC_UPSCALE = 2 };
+struct AdalnSrc {
+    const float* x_hat; const float* coef; int coef_stride; const float* a; const float* wx; const float* bx;   // SRC_PRECOND
+    const float* up; const int* atom2tok; int St_pad;                                                           // SRC_UPSCALE
+    int Na;
+};
+template <int C, int SRC>
+__global__ void __launch_bounds__(256) adaln_kernel(float* __restrict__ x, const float* __restrict__ mod,
                                                     int mod_stride, int mod_off, __half* __restrict__ xh,
-                                                    __half* __restrict__ xl, int rows, int S_pad, float eps) {
+                                                    __half* __restrict__ xl, int rows, int S_pad, float eps, AdalnSrc src) {
     griddep_launch();
     griddep_wait();
     constexpr int V = C / 128;     // float4 per lane
+    static_assert(SRC == SRC_X || C == 128, "fused sources exist for the atom width only");
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
-    const float4* src = reinterpret_cast<const float4*>(x + (size_t)row * C);
+    float4* xrow = reinterpret_cast<float4*>(x + (size_t)row * C);
     float4 v[V];
+    if constexpr (SRC == SRC_PRECOND) {
+        const int b = row / S_pad, s = row - b * S_pad;
+        float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (s < src.Na) {
+            const float c_in = src.coef[src.coef_stride * b];
+            const float* xp = src.x_hat + ((size_t)b * src.Na + s) * 3;
+            const float x0 = xp[0] * c_in, x1 = xp[1] * c_in, x2 = xp[2] * c_in;
+            const float4 av = *reinterpret_cast<const float4*>(src.a + (size_t)s * C + 4 * lane);
+            const float4 bv = *reinterpret_cast<const float4*>(src.bx + 4 * lane);
+            const float* w = src.wx + (size_t)(4 * lane) * 3;
+            out.x = fmaf(x2, w[2], fmaf(x1, w[1], x0 * w[0])) + bv.x + av.x;
+            out.y = fmaf(x2, w[5], fmaf(x1, w[4], x0 * w[3])) + bv.y + av.y;
+            out.z = fmaf(x2, w[8], fmaf(x1, w[7], x0 * w[6])) + bv.z + av.z;
+            out.w = fmaf(x2, w[11], fmaf(x1, w[10], x0 * w[9])) + bv.w + av.w;
+        }
+        v[0] = out;
+        xrow[lane] = out;
+    } else if constexpr (SRC == SRC_UPSCALE) {
+        const int b = row / S_pad, s = row - b * S_pad;
+        float4 cur = xrow[lane];
+        if (s < src.Na) {
+            const int tok = src.atom2tok[s];
+            const float4 u = *(reinterpret_cast<const float4*>(src.up + ((size_t)b * src.St_pad + tok) * C) + lane);
+            cur.x += u.x; cur.y += u.y; cur.z += u.z; cur.w += u.w;
+            xrow[lane] = cur;
+        }
+        v[0] = cur;
+    } else {
+#pragma unroll
+        for (int i = 0; i < V; ++i) v[i] = xrow[lane + 32 * i];
+    }
     float sum = 0.f;
 #pragma unroll
-    for (int i = 0; i < V; ++i) {
-        v[i] = src[lane + 32 * i];
-        sum += v[i].x + v[i].y + v[i].z + v[i].w;
-    }
+    for (int i = 0; i < V; ++i) sum += v[i].x + v[i].y + v[i].z + v[i].w;
     const float mean = warp_sum(sum) * (1.f / C);
     float sq = 0.f;
 #pragma unroll
@@ -327,12 +367,36 @@ cudaError_t launch_adaln(const float* x, const float* mod, int mod_stride, int m
                          int B, int S_pad, int c, float eps, cudaStream_t st) {
     const int rows = B * S_pad;
     if (rows <= 0 || (mod_off % 4) || (mod_stride % 4)) return cudaErrorInvalidValue;
+    const AdalnSrc none{};
+    float* xm = const_cast<float*>(x);       // SRC_X never writes x
     if (c == 128)
-        PDK_LAUNCH_CHECK(launch_pdl(adaln_kernel<128>, dim3((rows + 7) / 8), dim3(256), (size_t)(0), st, x, mod, mod_stride, mod_off, xh, xl, rows, S_pad, eps));
+        PDK_LAUNCH_CHECK(launch_pdl(adaln_kernel<128, SRC_X>, dim3((rows + 7) / 8), dim3(256), (size_t)(0), st, xm, mod, mod_stride, mod_off, xh, xl, rows, S_pad, eps, none));
     else if (c == 512)
-        PDK_LAUNCH_CHECK(launch_pdl(adaln_kernel<512>, dim3((rows + 7) / 8), dim3(256), (size_t)(0), st, x, mod, mod_stride, mod_off, xh, xl, rows, S_pad, eps));
+        PDK_LAUNCH_CHECK(launch_pdl(adaln_kernel<512, SRC_X>, dim3((rows + 7) / 8), dim3(256), (size_t)(0), st, xm, mod, mod_stride, mod_off, xh, xl, rows, S_pad, eps, none));
     else
         return cudaErrorInvalidValue;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_precond_adaln(const float* x_hat, const float* coef, int coef_stride, const float* a, const float* wx,
+                                 const float* bx, float* ba, const float* mod, int mod_stride, int mod_off, __half* xh,
+                                 __half* xl, int B, int Na, int S_pad, int c_a, float eps, cudaStream_t st) {
+    const int rows = B * S_pad;
+    if (rows <= 0 || c_a != 128 || Na > S_pad || (mod_off % 4) || (mod_stride % 4)) return cudaErrorInvalidValue;
+    AdalnSrc src{};
+    src.x_hat = x_hat; src.coef = coef; src.coef_stride = coef_stride; src.a = a; src.wx = wx; src.bx = bx; src.Na = Na;
+    PDK_LAUNCH_CHECK(launch_pdl(adaln_kernel<128, SRC_PRECOND>, dim3((rows + 7) / 8), dim3(256), (size_t)(0), st, ba, mod, mod_stride, mod_off, xh, xl, rows, S_pad, eps, src));
+    return cudaGetLastError();
+}
+
+cudaError_t launch_upscale_adaln(float* ba, const float* up, const int* atom2tok, const float* mod, int mod_stride,
+                                 int mod_off, __half* xh, __half* xl, int B, int Na, int Sa_pad, int St_pad, int c_a,
+                                 float eps, cudaStream_t st) {
+    const int rows = B * Sa_pad;
+    if (rows <= 0 || c_a != 128 || Na > Sa_pad || (mod_off % 4) || (mod_stride % 4)) return cudaErrorInvalidValue;
+    AdalnSrc src{};
+    src.up = up; src.atom2tok = atom2tok; src.St_pad = St_pad; src.Na = Na;
+    PDK_LAUNCH_CHECK(launch_pdl(adaln_kernel<128, SRC_UPSCALE>, dim3((rows + 7) / 8), dim3(256), (size_t)(0), st, ba, mod, mod_stride, mod_off, xh, xl, rows, Sa_pad, eps, src));
     return cudaGetLastError();
 }
 

@@ -86,6 +86,14 @@ cudaError_t launch_mod_gemv(const float* tsilu, const float* wmod, const float* 
 // x[B*S_pad, c] -> planes: LN_noaffine(x) * (1 + scale) + shift, (shift, scale) = mod[b, off .. off+2c)
 cudaError_t launch_adaln(const float* x, const float* mod, int mod_stride, int mod_off, __half* xh, __half* xl,
                          int B, int S_pad, int c, float eps, cudaStream_t st);
+// The first AdaLN of the atom encoder fused with AF3DiT.precond (ba rows are produced, stored and normalised in one pass) ...
+cudaError_t launch_precond_adaln(const float* x_hat, const float* coef, int coef_stride, const float* a, const float* wx,
+                                 const float* bx, float* ba, const float* mod, int mod_stride, int mod_off, __half* xh,
+                                 __half* xl, int B, int Na, int S_pad, int c_a, float eps, cudaStream_t st);
+// ... and the first AdaLN of the atom decoder fused with AF3DiT.upscale's gather-add (ba += up[atom2tok], stored, normalised)
+cudaError_t launch_upscale_adaln(float* ba, const float* up, const int* atom2tok, const float* mod, int mod_stride,
+                                 int mod_off, __half* xh, __half* xl, int B, int Na, int Sa_pad, int St_pad, int c_a,
+                                 float eps, cudaStream_t st);
 // x[rows, c] fp32 -> planes
 cudaError_t launch_split(const float* x, __half* xh, __half* xl, size_t n, cudaStream_t st);
 // ba[B,S_pad,c_a] = W_x (x_hat * c_in) + b_x + a   (rows >= Na zeroed)

@@ -192,3 +192,30 @@ def denoise_out(ba, x_hat, coef, ln_w, ln_b, wr, eps: float):
                                       _lib.ptr(ln_w.contiguous()), _lib.ptr(ln_b.contiguous()), _lib.ptr(wr.contiguous()),
                                       _lib.ptr(out), B, Na, S_pad, c_a, eps, _lib.stream_ptr(ba.device)), "denoise_out")
     return out
+
+
+def precond_adaln(x_hat, coef, a, wx, bx, S_pad: int, mod, mod_off: int, eps: float):
+    """The first AdaLN of the atom encoder with AF3DiT.precond fused in: returns (ba, hi, lo)."""
+    lib = _lib.load()
+    B, Na, _ = x_hat.shape
+    c_a = a.shape[1]
+    ba = torch.empty(B, S_pad, c_a, dtype=torch.float32, device=x_hat.device)
+    hi = torch.empty(B, S_pad, c_a, dtype=torch.float16, device=x_hat.device)
+    lo = torch.empty_like(hi)
+    _lib.check(lib.pdk_op_precond_adaln(_lib.ptr(x_hat.contiguous()), _lib.ptr(coef), _lib.ptr(a.contiguous()),
+                                        _lib.ptr(wx.contiguous()), _lib.ptr(bx.contiguous()), _lib.ptr(ba),
+                                        _lib.ptr(mod.contiguous()), mod.shape[1], mod_off, _lib.ptr(hi), _lib.ptr(lo), B, Na,
+                                        S_pad, c_a, eps, _lib.stream_ptr(x_hat.device)), "precond_adaln")
+    return ba, hi, lo
+
+
+def upscale_adaln(ba, up, atom2tok, Na: int, mod, mod_off: int, eps: float):
+    """The first AdaLN of the atom decoder with the upscale gather-add fused in: ba is updated in place; returns (ba, hi, lo)."""
+    lib = _lib.load()
+    B, Sa_pad, c_a = ba.shape
+    hi = torch.empty(B, Sa_pad, c_a, dtype=torch.float16, device=ba.device)
+    lo = torch.empty_like(hi)
+    _lib.check(lib.pdk_op_upscale_adaln(_lib.ptr(ba), _lib.ptr(up.contiguous()), _lib.ptr(atom2tok), _lib.ptr(mod.contiguous()),
+                                        mod.shape[1], mod_off, _lib.ptr(hi), _lib.ptr(lo), B, Na, Sa_pad, up.shape[1], c_a, eps,
+                                        _lib.stream_ptr(ba.device)), "upscale_adaln")
+    return ba, hi, lo

@@ -47,8 +47,8 @@ def test_handle_lifecycle_and_sizes_without_gpu(lib):
     assert ab.value == 6 * 4 * 2048 * 2048 * 4 and tb.value == 12 * 16 * 256 * 256 * 4     # 403 MB + 50 MB
     assert lib.pdk_dit_workspace_bytes(h, 16, 2048, 256, C.byref(ws)) == 0
     assert 100e6 < ws.value < 2e9
-    assert lib.pdk_dit_launches_per_denoise(h) == 3 + 5 * 6 + 7 * 12 + 7     # atom transition fused
-    assert lib.pdk_dit_launches_per_denoise_cond(h) == 1 + 5 * 6 + 7 * 12 + 7     # conditioning hoisted out of the step
+    assert lib.pdk_dit_launches_per_denoise(h) == 2 + 5 * 6 + 7 * 12 + 6     # atom transition fused; precond / gather-add ride in an AdaLN
+    assert lib.pdk_dit_launches_per_denoise_cond(h) == 5 * 6 + 7 * 12 + 6     # conditioning hoisted out of the step
     assert lib.pdk_dit_cond_width(h) == 41472 + 8
     cb = C.c_size_t()
     assert lib.pdk_dit_conditioning_workspace_bytes(h, 40, C.byref(cb)) == 0 and cb.value == 2 * 128 * 256 * 2

@@ -269,6 +269,28 @@ def test_precond_downscale_upscale_denoise(env):
     rel_close("denoise", xd, k["denoise_out"], rtol=0, atol=3e-6 * float(k["denoise_out"].abs().max()))
 
 
+def test_fused_adaln_sources_are_bit_identical(env):
+    """precond / upscale gather-add fused into the first AdaLN of their atom stack == the stand-alone kernels, bit for bit."""
+    from tests import pdk_ops as ops
+    dims, sd, dit, k = env
+    P = dit._packed
+    _, coef = ops.time_embed(k["k_t_hat"], P["freq"], P["te_w1"], P["te_b1"], P["te_w2"], P["te_b2"], 16.0)
+    g = torch.Generator(device=DEV).manual_seed(12)
+    mod = torch.randn(2, dit._n_mod, generator=g, device=DEV) * 0.3
+    off = int(dit._block_array[0].mod_attn_off)
+    ba = ops.precond(k["k_x_hat"], coef, k["k_a"], P["wx"], P["bx"], 128)
+    hi, lo = ops.adaln(ba, mod, off, dims.eps)
+    ba2, hi2, lo2 = ops.precond_adaln(k["k_x_hat"], coef, k["k_a"], P["wx"], P["bx"], 128, mod, off, dims.eps)
+    assert torch.equal(ba, ba2) and torch.equal(hi, hi2) and torch.equal(lo, lo2)
+    bap = pad_rows(k["ba"], 128)
+    up = torch.randn(2, 128, 128, generator=g, device=DEV)
+    a2t = k["a2t"].int().contiguous()
+    want = ops.gather_add(bap.clone(), up, a2t, 75)
+    hi, lo = ops.adaln(want, mod, off, dims.eps)
+    got, hi2, lo2 = ops.upscale_adaln(bap.clone(), up, a2t, 75, mod, off, dims.eps)
+    assert torch.equal(want, got) and torch.equal(hi, hi2) and torch.equal(lo, lo2)
+
+
 # ------------------------------------------------------------------------------------- coordinates / physics
 def test_centre_random_augmentation(env):
     from physdock_b200 import sampler as S
