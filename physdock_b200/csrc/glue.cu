@@ -170,17 +170,19 @@ __global__ void __launch_bounds__(256) adaln_kernel(float* __restrict__ x, const
 #pragma unroll
         for (int i = 0; i < V; ++i) v[i] = xrow[lane + 32 * i];
     }
+    // explicit rounding (no compiler-chosen FMA contraction): every instantiation of this kernel produces the same bits
     float sum = 0.f;
 #pragma unroll
-    for (int i = 0; i < V; ++i) sum += v[i].x + v[i].y + v[i].z + v[i].w;
-    const float mean = warp_sum(sum) * (1.f / C);
+    for (int i = 0; i < V; ++i) sum = __fadd_rn(sum, __fadd_rn(__fadd_rn(v[i].x, v[i].y), __fadd_rn(v[i].z, v[i].w)));
+    const float mean = __fmul_rn(warp_sum(sum), 1.f / C);
     float sq = 0.f;
 #pragma unroll
     for (int i = 0; i < V; ++i) {
-        v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
-        sq += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+        v[i].x = __fsub_rn(v[i].x, mean); v[i].y = __fsub_rn(v[i].y, mean);
+        v[i].z = __fsub_rn(v[i].z, mean); v[i].w = __fsub_rn(v[i].w, mean);
+        sq = fmaf(v[i].x, v[i].x, fmaf(v[i].y, v[i].y, fmaf(v[i].z, v[i].z, fmaf(v[i].w, v[i].w, sq))));
     }
-    const float rstd = inv_sqrt(warp_sum(sq) * (1.f / C) + eps);
+    const float rstd = inv_sqrt(__fadd_rn(__fmul_rn(warp_sum(sq), 1.f / C), eps));
     const float* shift = mod + (size_t)(row / S_pad) * mod_stride + mod_off;
     const float* scale = shift + C;
 #pragma unroll
@@ -188,10 +190,10 @@ __global__ void __launch_bounds__(256) adaln_kernel(float* __restrict__ x, const
         const int c0 = 4 * (lane + 32 * i);
         const float4 sh = *reinterpret_cast<const float4*>(shift + c0);
         const float4 sc = *reinterpret_cast<const float4*>(scale + c0);
-        const float y0 = v[i].x * rstd * (1.f + sc.x) + sh.x;
-        const float y1 = v[i].y * rstd * (1.f + sc.y) + sh.y;
-        const float y2 = v[i].z * rstd * (1.f + sc.z) + sh.z;
-        const float y3 = v[i].w * rstd * (1.f + sc.w) + sh.w;
+        const float y0 = fmaf(__fmul_rn(v[i].x, rstd), __fadd_rn(1.f, sc.x), sh.x);
+        const float y1 = fmaf(__fmul_rn(v[i].y, rstd), __fadd_rn(1.f, sc.y), sh.y);
+        const float y2 = fmaf(__fmul_rn(v[i].z, rstd), __fadd_rn(1.f, sc.z), sh.z);
+        const float y3 = fmaf(__fmul_rn(v[i].w, rstd), __fadd_rn(1.f, sc.w), sh.w);
         uint2 hi, lo;
         split2(y0, y1, hi.x, lo.x);
         split2(y2, y3, hi.y, lo.y);
