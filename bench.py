@@ -170,9 +170,12 @@ def attention_dram_traffic():
     return None, None
 
 
-def time_attention_kernel(dit, B, iters=12):
-    """Average duration of the dominant kernel (atom pair-bias attention) measured with CUDA events on the
-    launching stream; the 6 cached bias blocks (67 MB each) are cycled so no launch finds its bias in L2."""
+def time_attention_kernel(dit, B, rounds=2):
+    """Average launch duration of the dominant kernel (atom pair-bias attention) as the step runs it: launched back to
+    back from a CUDA graph with Programmatic Dependent Launch, cycling the 6 cached bias blocks of the prepared complex
+    (67 MB each, 403 MB > L2: no launch finds its bias in L2); CUDA events around the replay on the launching stream.
+    Also returns the duration with an event recorded after EVERY launch (cold start of each launch exposed; round 1's
+    method), reported as `launch_ms_isolated`."""
     from physdock_b200 import _lib
     lib = _lib.load()
     dev = torch.device("cuda", torch.cuda.current_device())
@@ -183,22 +186,38 @@ def time_attention_kernel(dit, B, iters=12):
     oh = torch.empty(B * S_pad, H * 32, dtype=torch.float16, device=dev)
     ol = torch.empty_like(oh)
     bias = dit._complex_keep["bias_a"].view(-1, H, S_pad, S_pad)
-    st = _lib.stream_ptr(dev)
+    n_blocks = bias.shape[0]
 
     def launch(l):
-        _lib.check(lib.pdk_op_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), bias[l % bias.shape[0]].data_ptr(),
-                                        oh.data_ptr(), ol.data_ptr(), B, H, S_pad, st), "pdk_op_attention")
+        _lib.check(lib.pdk_op_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), bias[l % n_blocks].data_ptr(),
+                                        oh.data_ptr(), ol.data_ptr(), B, H, S_pad, _lib.stream_ptr(dev)), "pdk_op_attention")
     for l in range(3):
         launch(l)
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(iters + 1)]
+    torch.cuda.synchronize()
+    n = rounds * n_blocks
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        for i in range(n):
+            launch(i)
+    graph.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = []
+    for _ in range(5):
+        e0.record()
+        graph.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        reps.append(e0.elapsed_time(e1) / n)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
     ev[0].record()
-    for i in range(iters):
+    for i in range(n):
         launch(i)
         ev[i + 1].record()
     torch.cuda.synchronize()
-    ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(iters)]
+    isolated = statistics.mean(ev[i].elapsed_time(ev[i + 1]) for i in range(n))
     flops = B * H * 4 * S * S * 32          # QK^T + PV, 2 flop per MAC (algorithmic, not the 3x split)
-    return statistics.mean(ms) * 1e-3, flops
+    return statistics.median(reps) * 1e-3, flops, isolated * 1e-3
 
 
 def parity_gate(smp, sd, cx_cpu, step_ids):
@@ -451,7 +470,7 @@ def main():
         smp.begin()          # the sampler shares the denoiser's workspace/graphs: leave it in a defined state
 
     peaks = measured_peaks()
-    t_attn, f_attn = time_attention_kernel(dit, B)
+    t_attn, f_attn, t_attn_iso = time_attention_kernel(dit, B)
     traffic, traffic_src = attention_dram_traffic()
     value = world * B * K / (ms_total * 1e-3)
     e2e = world * B * K / (ms_e2e * 1e-3)
@@ -482,6 +501,8 @@ def main():
                      "traffic_source": f"{traffic_src} (committed ncu --set full capture of this shape; not measured in this run)",
                      "issued_mma_tflops": 3 * f_attn / t_attn / 1e12,
                      "peak_source": peaks["source"] + ", burst bf16", "launch_ms": t_attn * 1e3,
+                     "launch_ms_isolated": t_attn_iso * 1e3,
+                     "timing": "average launch duration over a CUDA-graph replay of 12 back-to-back launches cycling the 6 cached bias blocks (as in the step); launch_ms_isolated = event after every launch",
                      "algorithmic_gflop_per_launch": f_attn / 1e9},
     }
     if shard_par is not None:
