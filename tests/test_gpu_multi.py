@@ -29,6 +29,22 @@ torch.manual_seed(3)
 x_one = sample_diffusion(dit, cx, cx["a"], cx["ap"], cx["s"], cx["z"], num_sample=5, **kw)
 assert x_all.shape == (5, 100, 3)
 assert torch.equal(x_all, x_one), float((x_all - x_one).abs().max())
+# the round driver in sharded mode (one all_gather_into_tensor per round) == the single-process driver, bit for bit
+from physdock_b200.rounds import run_rounds
+from physdock_b200.sampler import PhysDockB200
+from physdock_b200.synthetic import make_templates
+model = PhysDockB200(dit, diffusion_conditioning=lambda b: (b["a"], b["ap"], b["s"], b["z"]))
+lig = torch.nonzero(cx["is_ligand"][cx["atom_id_to_token_id"]].bool()).flatten()
+i0, i1, i2 = int(lig[0]), int(lig[1]), int(lig[2])
+accept = lambda x: float(torch.linalg.cross(x[i1] - x[i0], x[i2] - x[i0])[2]) > 0.0
+rk = dict(num_augmentation_sample=3, max_samples=5, max_rounds=3, steps=4, physics_correction=True, conformers=make_templates(cx, 9),
+          accept_fn=accept, ranking=False, seed=11)
+a = run_rounds(model, cx, sharded=True, **rk)
+b = run_rounds(model, cx, sharded=False, **rk)
+assert len(a.rounds) == len(b.rounds) and a.n_accepted == b.n_accepted
+assert torch.equal(a.accept_samples, b.accept_samples)
+for ra, rb in zip(a.rounds, b.rounds):
+    assert ra.pass_flags == rb.pass_flags and torch.equal(ra.x_pred, rb.x_pred)
 dist.barrier(); dist.destroy_process_group()
 print("rank", rank, "ok")
 '''
