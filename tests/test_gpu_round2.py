@@ -223,3 +223,30 @@ def test_forward_on_wrong_device_is_loud(dit):
     with pytest.raises(PdkError):
         dit.denoise(torch.zeros(1, 512, 3, device="cuda:1"), torch.ones(1, device="cuda:1"))
     del cx
+
+
+def test_benchmarked_configuration_b16_256_2048_sampler_step(dit):
+    """The configuration bench.py times (Nt=256, Na=2048, B=16: 4+4+4+4 / 4+3+3+3+3 attention work list, > 148-tile persistent
+    GEMM loops, cta_group::2 tiles, CUDA-graph replay of pdk_dit_denoise_cond with the fused Euler update): one stochastic and
+    one ODE-tail step of DiffusionSampler.step, teacher-forced against the host oracle."""
+    from physdock_b200 import sampler as S
+    from physdock_b200.synthetic import DiTDims, make_complex
+    dims, sd, _ = medium_state()
+    cx = make_complex(256, 2048, DiTDims.named("medium"), seed=1)
+    d = to_dev(cx)
+    torch.manual_seed(5)
+    smp = S.DiffusionSampler(dit, d, d["a"], d["ap"], d["s"], d["z"], num_sample=16, steps=40,
+                             karras_noise_schedule_power=1000, align_ref_pos=False)
+    smp.begin()
+    for i in (2, 34):
+        smp.step(i)
+        t_cur, t_next, t_hat, stochastic, _ = smp.schedule(i)
+        x_hat, x_den, x_next = smp.x_hat.cpu(), smp.x_den.cpu(), smp.x_next.cpu()
+        th = torch.full([16], float(t_hat))
+        with torch.no_grad():
+            want = O.af3dit_forward(sd, cx, x_hat, th, cx["a"], cx["ap"], cx["s"], cx["z"])
+        want_next = O.euler_update(x_hat, (x_hat - want) / th[:, None, None], th, t_next, 1.5 if stochastic else 1.0)
+        r_den, r_next = float(O.rmsd(x_den, want).max()), float(O.rmsd(x_next, want_next).max())
+        log_value(f"B=16 256/2048 step {i}: x_denoised rmsd", r_den)
+        log_value(f"B=16 256/2048 step {i}: x_next rmsd", r_next)
+        assert r_den < TOL_A and r_next < TOL_A, (i, r_den, r_next)
