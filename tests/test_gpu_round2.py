@@ -239,6 +239,8 @@ def test_benchmarked_configuration_b16_256_2048_sampler_step(dit):
                              karras_noise_schedule_power=1000, align_ref_pos=False)
     smp.begin()
     for i in (2, 34):
+        if i == 34:      # a plausible late-step state: the structure plus noise at the step's sigma
+            smp.x_next.copy_(d["x_gt"][None] + float(smp.sigmas[i]) * torch.randn(16, 2048, 3, device=DEV))
         smp.step(i)
         t_cur, t_next, t_hat, stochastic, _ = smp.schedule(i)
         x_hat, x_den, x_next = smp.x_hat.cpu(), smp.x_den.cpu(), smp.x_next.cpu()
