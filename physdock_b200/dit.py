@@ -77,6 +77,7 @@ class B200DiT(nn.Module):
         self._graphs: Dict[tuple, object] = {}
         self._block_array = None
         self._fwd_static: Dict[tuple, tuple] = {}
+        self._bias_bufs = None
         self.use_cuda_graph = True
 
     # ------------------------------------------------------------------ construction helpers
@@ -250,8 +251,16 @@ class B200DiT(nn.Module):
             raise _lib.PdkError("token_id_to_chunk_sizes / atom_id_to_token_id inconsistent with a, s")
         ab, tb = C.c_size_t(), C.c_size_t()
         _lib.check(lib.pdk_dit_bias_bytes(self._handle, Na, Nt, C.byref(ab), C.byref(tb)), "pdk_dit_bias_bytes")
-        bias_a = torch.empty(ab.value // 4, dtype=torch.float32, device=dev)
-        bias_t = torch.empty(tb.value // 4, dtype=torch.float32, device=dev)
+        # the two bias caches (403 MB + 50 MB at 2048 / 256) are persistent buffers of this module, reused for the next complex
+        # when they are large enough (a fresh 453 MB allocation per screening ligand cost milliseconds of cudaMalloc / free)
+        self._graphs.clear()                  # captured graphs read the buffers about to be overwritten
+        bufs = self._bias_bufs
+        if bufs is None or bufs[0].numel() < ab.value // 4 or bufs[1].numel() < tb.value // 4 or bufs[0].device != dev:
+            self._bias_bufs = bufs = None
+            self._complex_keep = None         # release the previous caches before allocating the new ones
+            bufs = self._bias_bufs = (torch.empty(ab.value // 4, dtype=torch.float32, device=dev),
+                                      torch.empty(tb.value // 4, dtype=torch.float32, device=dev))
+        bias_a, bias_t = bufs[0][: ab.value // 4], bufs[1][: tb.value // 4]
         _lib.check(lib.pdk_dit_prepare_complex(self._handle, _lib.ptr(a_), _lib.ptr(ap_), _lib.ptr(s_), _lib.ptr(z_),
                                                _lib.ptr(apm), _lib.ptr(zm), _lib.ptr(tok_start), _lib.ptr(atom2tok),
                                                Na, Nt, _lib.ptr(bias_a), _lib.ptr(bias_t), _lib.stream_ptr(dev)),

@@ -49,7 +49,7 @@ def test_full_40_step_reference_trace_teacher_forced(dit, name):
     trace = []
     x = S.sample_diffusion(dit, d, d["a"], d["ap"], d["s"], d["z"], num_sample=2, steps=40,
                            karras_noise_schedule_power=1000, rng=O.ReplayRNG(tape, DEV), trace=trace,
-                           teacher=ref_trace, **kw)
+                           teacher=ref_trace, use_cuda_graph=(name == "nophys"), **kw)      # one trace per launch mode
     assert len(trace) == 40 and sum(1 for st in trace if st["t_cur"] > 1.0) == 29
     worst_den = worst_next = 0.0
     for i, (mine, ref) in enumerate(zip(trace, ref_trace)):
@@ -196,7 +196,7 @@ def test_graphs_survive_workspace_growth(dit):
 
     def run(n):
         torch.manual_seed(21)
-        smp = S.DiffusionSampler(dit, cx, cx["a"], cx["ap"], cx["s"], cx["z"], num_sample=n, **kw)
+        smp = S.DiffusionSampler(dit, cx, cx["a"], cx["ap"], cx["s"], cx["z"], num_sample=n, use_cuda_graph=True, **kw)
         smp.begin()
         return smp, [smp.step(i).clone() for i in range(3)]
 
@@ -236,7 +236,7 @@ def test_benchmarked_configuration_b16_256_2048_sampler_step(dit):
     d = to_dev(cx)
     torch.manual_seed(5)
     smp = S.DiffusionSampler(dit, d, d["a"], d["ap"], d["s"], d["z"], num_sample=16, steps=40,
-                             karras_noise_schedule_power=1000, align_ref_pos=False)
+                             karras_noise_schedule_power=1000, align_ref_pos=False, use_cuda_graph=True)
     smp.begin()
     for i in (2, 34):
         if i == 34:      # a plausible late-step state: the structure plus noise at the step's sigma

@@ -21,7 +21,7 @@ if physics:
     field = PairEnergyField(cx["a_mask"], f["sigma"], f["eps"], f["partner"], f["partner_r0"], f["partner_k"], rows=f["rows"])
     kw = dict(align_ref_pos=True, ref_mol_poses=make_templates(cx, 40), mmff_gamma_0_factor=6.0, physics_field=field, mmff_iters=5)
 torch.manual_seed(0)
-smp = DiffusionSampler(dit, cx, cx["a"], cx["ap"], cx["s"], cx["z"], num_sample=B, steps=40, karras_noise_schedule_power=1000, **kw)
+smp = DiffusionSampler(dit, cx, cx["a"], cx["ap"], cx["s"], cx["z"], num_sample=B, steps=40, karras_noise_schedule_power=1000, use_cuda_graph=True, **kw)
 smp.begin()
 steps = list(range(3)) + list(range(30, 33))           # early (stochastic, template projection) and late (descent) steps
 for i in steps: smp.step(i)

@@ -20,7 +20,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     dit = B200DiT.from_state_dict(make_dit_state(dims, seed=0), dims, device=dev)
     cx = {k: v.to(dev) for k, v in make_complex(256, 2048, dims, seed=1).items()}
     torch.manual_seed(0)
-    smp = DiffusionSampler(dit, cx, cx["a"], cx["ap"], cx["s"], cx["z"], num_sample=16, steps=40, karras_noise_schedule_power=1000, align_ref_pos=False)
+    smp = DiffusionSampler(dit, cx, cx["a"], cx["ap"], cx["s"], cx["z"], num_sample=16, steps=40, karras_noise_schedule_power=1000, align_ref_pos=False, use_cuda_graph=True)
     smp.begin()
     for i in range(4): smp.step(i)
     torch.cuda.synchronize()
