@@ -2,8 +2,9 @@
 # A/B of two library builds on ONE GPU box (box-to-box spread is ~1.5 %, so variants must share a box):
 #   build the variant with a -D switch into build/dbg/libpdk_<NAME>.so here (see tools/gemm_variants.sh), then
 #   gpurun -- 'VARIANTS="NAME1 NAME2" bash tools/gpu_ab.sh'
-# Measurement switches read at run time: PDK_NO_PAIR, PDK_FORCE_PAIR, PDK_NO_WIDE, PDK_WIDE_ALL, PDK_NO_ATTN_BALANCE,
-# PDK_NO_FUSED_TRANSITION, PDK_NO_PDL, PDK_NO_GRAPH.
+# Measurement switches (PDK_NO_PAIR, PDK_FORCE_PAIR, PDK_NO_WIDE, PDK_WIDE_ALL, PDK_NO_ATTN_BALANCE, PDK_NO_FUSED_TRANSITION,
+# PDK_NO_PDL) are read from the environment ONLY by the debug variants (built with -DPDK_MEASURE by tools/gemm_variants.sh);
+# the release library ignores them.  Graph vs eager launches: DiffusionSampler(use_cuda_graph=...).
 mkdir -p gpurun_out
 {
 for rep in 1 2; do
