@@ -10,6 +10,7 @@ from physdock_b200.synthetic import DiTDims, make_dit_state, make_complex, make_
 from physdock_b200.physics import PairEnergyField
 cfg = sys.argv[1] if len(sys.argv) > 1 else "C3"
 Nt, Na, B, physics = {"C1": (64, 512, 4, False), "C3": (384, 3072, 64, True), "C5": (256, 2048, 5, False)}[cfg]
+if len(sys.argv) > 2: B = int(sys.argv[2])            # optional batch override: python tools/run_config.py C5 8
 dev = torch.device("cuda")
 dims = DiTDims.named("medium")
 dit = B200DiT.from_state_dict(make_dit_state(dims, seed=0), dims, device=dev)
