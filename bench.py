@@ -182,7 +182,13 @@ def time_attention_kernel(dit, B, rounds=2):
     H, S = 4, dit._complex_keep["Na"]
     S_pad = int(lib.pdk_pad_len(S))
     g = torch.Generator(device=dev).manual_seed(0)
-    q, k, v = (torch.randn(B, H, S_pad, 64, generator=g, device=dev).half() for _ in range(3))
+
+    def planes(scale):            # [B,H,S_pad,64] rows [hi 32 | lo 32] of an fp32 tensor, as the QKV GEMM epilogue writes them
+        x = torch.randn(B, H, S_pad, 32, generator=g, device=dev) * scale
+        hi = x.half()
+        return torch.cat([hi, (x - hi.float()).half()], -1).contiguous()
+    # unit-RMS q and k (the model RMS-normalises both), q pre-scaled by log2(e) / sqrt(32) as the epilogue does
+    q, k, v = planes(1.4427 / 32 ** 0.5), planes(1.0), planes(1.0)
     oh = torch.empty(B * S_pad, H * 32, dtype=torch.float16, device=dev)
     ol = torch.empty_like(oh)
     bias = dit._complex_keep["bias_a"].view(-1, H, S_pad, S_pad)
@@ -240,10 +246,52 @@ def parity_gate(smp, sd, cx_cpu, step_ids):
             r_den, r_next = float(O.rmsd(x_den, want_den).max()), float(O.rmsd(x_next, want_next).max())
             per_step.append({"step": i, "t_hat": float(t_hat), "x_denoised_rmsd": r_den, "x_next_rmsd": r_next})
             worst_den, worst_next = max(worst_den, r_den), max(worst_next, r_next)
-    out = {"x_denoised_rmsd": worst_den, "x_next_rmsd": worst_next, "B": smp.B, "Nt": NT, "Na": NA, "tolerance_A": 1e-3,
+    out = {"x_denoised_rmsd": worst_den, "x_next_rmsd": worst_next, "B": smp.B, "Nt": int(cx_cpu["s"].shape[0]),
+           "Na": int(cx_cpu["a"].shape[0]), "tolerance_A": 1e-3,
            "oracle": "oracle/physdock_oracle.py on the host (fp32, bit-identical to the reference)", "steps": per_step,
            "path": "DiffusionSampler.step -> CUDA graph of pdk_dit_denoise_cond (the timed path)"}
     assert worst_den < 1e-3 and worst_next < 1e-3, f"parity gate failed: {out}"
+    return out
+
+
+def other_config(dit, sd, dims, dev, Nt, Na, Bc, W, physics, what):
+    """One of the other BASELINE.json configurations on this GPU (context, not the headline): a 40-step run of the device-resident
+    step at that shape; without physics also the parity gate of that shape (one stochastic step against the CPU oracle)."""
+    from physdock_b200.sampler import DiffusionSampler
+    from physdock_b200.synthetic import make_complex
+    cx_cpu = make_complex(Nt, Na, dims, seed=1)
+    cx = {k: v.to(dev) for k, v in cx_cpu.items()}
+    kw = dict(align_ref_pos=False)
+    if physics:
+        from physdock_b200.synthetic import make_templates, make_ligand_field
+        from physdock_b200.physics import PairEnergyField
+        n_lig = int(cx["is_ligand"][cx["atom_id_to_token_id"]].sum())
+        f = make_ligand_field(Na, n_lig, seed=2, missing=False)
+        field = PairEnergyField(cx["a_mask"], f["sigma"], f["eps"], f["partner"], f["partner_r0"], f["partner_k"], rows=f["rows"])
+        kw = dict(align_ref_pos=True, ref_mol_poses=make_templates(cx, 40), mmff_gamma_0_factor=6.0, physics_field=field, mmff_iters=5)
+    torch.manual_seed(5)
+    smp = DiffusionSampler(dit, cx, cx["a"], cx["ap"], cx["s"], cx["z"], num_sample=Bc, steps=SCHED_STEPS,
+                           karras_noise_schedule_power=RHO, use_cuda_graph=True, **kw)
+    out = {"workload": what, "Nt": Nt, "Na": Na, "samples": Bc}
+    if physics:
+        out["parity"] = "unpinned (pair-energy physics backend has no reference arithmetic)"
+    else:
+        par = parity_gate(smp, sd, cx_cpu, step_ids=(1,))
+        out["parity"] = {"x_denoised_rmsd": par["x_denoised_rmsd"], "x_next_rmsd": par["x_next_rmsd"], "tolerance_A": 1e-3}
+    smp.begin()
+    for i in range(W):
+        smp.step(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    smp.begin()
+    e0.record()
+    for i in range(SCHED_STEPS):
+        x = smp.step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    assert torch.isfinite(x).all()
+    ms = e0.elapsed_time(e1) / SCHED_STEPS
+    out.update(ms_per_step=ms, sample_steps_per_s=Bc / (ms * 1e-3), gpu_launches_per_step=smp.launches_per_step(0))
     return out
 
 
@@ -341,6 +389,11 @@ def main():
     parity = None
     if not args.no_parity and rank == 0 and not args.physics:
         parity = parity_gate(smp, sd, cx_cpu, step_ids=(1, 33))       # a stochastic step (t_hat ~ 3.7e3 A) and an ODE-tail step
+    # the dominant kernel timed ALONE (roofline against the burst peak, which MEASURED_PEAKS.json also took on an idle chip):
+    # before the sustained regions, which leave the chip in sw_power_cap at ~1750 MHz
+    t_attn = f_attn = t_attn_iso = None
+    if rank == 0:
+        t_attn, f_attn, t_attn_iso = time_attention_kernel(dit, B)
     shard_par = None
     if world > 1:
         warm_communicator(dev)
@@ -468,9 +521,18 @@ def main():
         extras["dit_forward_call"] = {"api": "B200DiT.forward(batch, x_hat, t_hat, a, ap, s, z) (model.py:153,221 seam), CUDA-graph replay",
                                       "ms_per_call": e0.elapsed_time(e1) / 20}
         smp.begin()          # the sampler shares the denoiser's workspace/graphs: leave it in a defined state
+        if world == 1:
+            # the other single-complex configurations of BASELINE.json, one 40-step run each (these re-prepare the denoiser for
+            # another complex: nothing below uses the benchmark complex's caches any more)
+            extras["other_configs"] = {
+                "C1": other_config(dit, sd, dims, dev, 64, 512, 4, W, False,
+                                   "BASELINE.json configs[0]: crop 64 / atom crop 512, 4 samples, physics off (synthetic features)"),
+                "C3": other_config(dit, sd, dims, dev, 384, 3072, 64, W, True,
+                                   "BASELINE.json configs[2]: crop 384 / atom crop 3072, 64 samples, RDKit-free physics guidance "
+                                   "(40 templates, Kabsch projection, late steps: pair-energy descent; parity vs RDKit MMFF94 UNPINNED)"),
+            }
 
     peaks = measured_peaks()
-    t_attn, f_attn, t_attn_iso = time_attention_kernel(dit, B)
     traffic, traffic_src = attention_dram_traffic()
     value = world * B * K / (ms_total * 1e-3)
     e2e = world * B * K / (ms_e2e * 1e-3)
@@ -502,7 +564,7 @@ def main():
                      "issued_mma_tflops": 3 * f_attn / t_attn / 1e12,
                      "peak_source": peaks["source"] + ", burst bf16", "launch_ms": t_attn * 1e3,
                      "launch_ms_isolated": t_attn_iso * 1e3,
-                     "timing": "average launch duration over a CUDA-graph replay of 12 back-to-back launches cycling the 6 cached bias blocks (as in the step); launch_ms_isolated = event after every launch",
+                     "timing": "kernel timed alone before the sustained regions: average launch duration over a CUDA-graph replay of 12 back-to-back launches cycling the 6 cached bias blocks (as in the step); launch_ms_isolated = event after every launch",
                      "algorithmic_gflop_per_launch": f_attn / 1e9},
     }
     if shard_par is not None:
