@@ -111,3 +111,46 @@ def test_cpu_tensors_fail_loudly(dit):
     cx = complex_64_512()
     with pytest.raises(PdkError):
         dit(cx, torch.zeros(1, 512, 3), torch.ones(1), cx["a"], cx["ap"], cx["s"], cx["z"])
+
+
+@pytest.mark.parametrize("name", ["toy", "tiny", "small", "full"])
+def test_other_model_sizes_vs_oracle(name):
+    """The reference defines five model sizes that differ only in block counts (configs.py:63-93: toy 2+2/2, tiny 2+2/4,
+    small 2+2/8, medium 3+3/12, full 3+3/24 atom/token DiT blocks): the handle, the modulation table and the launch plan take
+    the counts from the dims.  Ragged complex, three noise levels, against the CPU oracle."""
+    from physdock_b200.dit import B200DiT
+    from physdock_b200.synthetic import make_dit_state
+    dims = DiTDims.named(name)
+    sd = make_dit_state(dims, seed=3)
+    dit = B200DiT.from_state_dict(sd, dims, device=DEV)
+    cx = make_complex(24, 100, dims, seed=11, ragged=True)
+    g = torch.Generator().manual_seed(5)
+    x_hat = torch.randn(3, 100, 3, generator=g) * 30
+    t_hat = torch.tensor([300.0, 5.0, 0.1])
+    with torch.no_grad():
+        want = O.af3dit_forward(sd, cx, x_hat, t_hat, cx["a"], cx["ap"], cx["s"], cx["z"])
+    d = to_dev(cx)
+    got = dit(d, x_hat.to(DEV), t_hat.to(DEV), d["a"], d["ap"], d["s"], d["z"]).cpu()
+    r = float(O.rmsd(got, want).max())
+    log_value(f"dit model={name} 24/100 rmsd", r)
+    assert r < TOL_A, (name, r)
+    n_atom, n_tok = 2 * dims.no_blocks_atom, dims.no_blocks_dit
+    assert dit.launches_per_denoise() == 2 + 5 * n_atom + 7 * n_tok + 6
+
+
+@pytest.mark.parametrize("Nt,Na,B", [(2, 5, 1), (3, 130, 1), (2, 5, 7)])
+def test_tiny_complexes_and_single_sample(dit, Nt, Na, B):
+    """Smallest inputs the feature pipeline can produce (a handful of atoms: every tile is almost all padding; a token
+    owning 129 atoms straddles a 128-row tile; a zero-size token) and B = 1."""
+    dims, sd, _ = medium_state()
+    cx = make_complex(Nt, Na, dims, seed=21, ragged=True)
+    g = torch.Generator().manual_seed(Na)
+    x_hat = torch.randn(B, Na, 3, generator=g) * 10
+    t_hat = torch.full([B], 40.0)
+    with torch.no_grad():
+        want = O.af3dit_forward(sd, cx, x_hat, t_hat, cx["a"], cx["ap"], cx["s"], cx["z"])
+    d = to_dev(cx)
+    got = dit(d, x_hat.to(DEV), t_hat.to(DEV), d["a"], d["ap"], d["s"], d["z"]).cpu()
+    r = float(O.rmsd(got, want).max())
+    log_value(f"dit tiny {Nt}/{Na} B={B} rmsd", r)
+    assert torch.isfinite(got).all() and r < TOL_A, (Nt, Na, B, r)
