@@ -295,6 +295,27 @@ def other_config(dit, sd, dims, dev, Nt, Na, Bc, W, physics, what):
     return out
 
 
+def screening_ligand_cost(dit, dims, dev, n_ligands=4, samples=8):
+    """BASELINE.json configs[3] (screening: 8 poses per ligand) as far as this path goes: wall time per ligand of the sampling
+    call alone -- a NEW complex every call (pair-bias prepass, conditioning, 40 steps, poses to the host), trunk excluded
+    (out of scope; measured against it in DESIGN.md section 7)."""
+    from physdock_b200.sampler import PhysDockB200
+    from physdock_b200.synthetic import make_complex
+    model = PhysDockB200(dit, diffusion_conditioning=lambda b: (b["a"], b["ap"], b["s"], b["z"]))
+    ligands = [{k: v.to(dev) for k, v in make_complex(NT, NA, dims, seed=100 + i).items()} for i in range(n_ligands + 1)]
+    times = []
+    for i, cx in enumerate(ligands):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        x = model.sample_diffusion(cx, num_sample=samples, steps=SCHED_STEPS, karras_noise_schedule_power=RHO, align_ref_pos=False).cpu()
+        times.append(time.perf_counter() - t0)
+        assert torch.isfinite(x).all()
+    per = statistics.median(times[1:])                    # the first call warms allocations
+    return {"workload": "BASELINE.json configs[3] per ligand: 8 poses x 40 steps at 256/2048 on one GPU, new complex per call, "
+                        "trunk and featurisation excluded", "samples": samples, "ms_per_ligand": per * 1e3,
+            "ligands_per_s_per_gpu": 1.0 / per, "sample_steps_per_s": samples * SCHED_STEPS / per}
+
+
 def sharded_parity(dit, cx, world, rank):
     """world > 1: `sample_diffusion_sharded(exact=True)` must reproduce, slice for slice and bit for bit, the samples
     a single process draws (ShardedRNG over NCCL); 2 steps, 4 samples per rank."""
@@ -527,6 +548,7 @@ def main():
             extras["other_configs"] = {
                 "C1": other_config(dit, sd, dims, dev, 64, 512, 4, W, False,
                                    "BASELINE.json configs[0]: crop 64 / atom crop 512, 4 samples, physics off (synthetic features)"),
+                "C4": screening_ligand_cost(dit, dims, dev),
                 "C3": other_config(dit, sd, dims, dev, 384, 3072, 64, W, True,
                                    "BASELINE.json configs[2]: crop 384 / atom crop 3072, 64 samples, RDKit-free physics guidance "
                                    "(40 templates, Kabsch projection, late steps: pair-energy descent; parity vs RDKit MMFF94 UNPINNED)"),
