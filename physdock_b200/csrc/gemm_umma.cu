@@ -8,12 +8,14 @@
 // (Al*Wh + Ah*Wl + Ah*Wh) accumulate in fp32 in TMEM.
 //
 // PERSISTENT kernel, 576 threads per CTA, warp-specialised.  Two tilings:
-//   PAIR (M % 256 == 0 and K*N >= 700k, i.e. the token SwiGLU / w2 / QKV shapes): a CLUSTER OF TWO CTAs owns a 256 x 128
+//   PAIR (M % 256 == 0 and K*N >= 250k, i.e. the token SwiGLU / w2 / QKV / out-proj shapes): a CLUSTER OF TWO CTAs owns a 256 x 128
 //        tile; each CTA loads its 128 rows of A and 64 of the 128 W rows, the leader issues tcgen05.mma.cta_group::2
 //        (M = 256) into both CTAs' TMEM.  Per CTA a stage is 48 KB for 768 MMA cycles instead of 64 KB (the single-CTA
 //        tiling is bound by TMA ingest, ~48 B/clk/SM against the 83 B/clk it needs).  Measured (tools/time_gemm.py):
-//        token SwiGLU 28.9 -> 26.4 us, token w2 21.0 -> 19.7 us; the K = 128 atom shapes LOSE 1-6 us to the cluster
-//        launch / two-CTA handshakes, so they stay on the single-CTA tiling.
+//        token SwiGLU 28.9 -> 26.4 us, token w2 21.0 -> 19.7 us, token out-proj (K = N = 512: 384 instead of 512 KB of
+//        operands per CTA) 10.5 -> 10.2 us at B = 16 and 9.7 -> 8.8 us at 4 samples of 64 tokens; the K = 128 atom shapes
+//        gain or lose a few tenths of a microsecond (atom out-proj always loses 0.6: cluster launch / two-CTA handshakes on
+//        tiles with 2 K-steps), so they stay on the single-CTA tiling (profiles/r02_gemm_tiling_policy.txt).
 //   single CTA: 128 x 128 tiles.
 // Tiles are walked n-fastest so concurrently running CTAs share the A tile in L2.  Roles:
 //   warp 0   : TMA producer: 4 plane tiles [128 rows x 64 halves] per stage, SWIZZLE_128B, ring of 3 stages (single CTA,
@@ -448,7 +450,7 @@ cudaError_t launch_one(const GemmArgs& a, cudaStream_t st) {
     // measurement switches: compile-time false in the release build (common.cuh)
     static const bool allow_pair = !measure_switch("PDK_NO_PAIR");
     static const bool force_pair = measure_switch("PDK_FORCE_PAIR");
-    const bool big = (long long)a.K * a.N >= 700000;       // see the header: small-K shapes lose on the pair tiling
+    const bool big = (long long)a.K * a.N >= 250000;       // see the header: the K = 128 atom shapes do not gain from the pair tiling
     static const bool allow_wide = !measure_switch("PDK_NO_WIDE");
     const bool pair = allow_pair && a.M % (2 * BM) == 0 && (big || force_pair);
     if constexpr (EPI == EPI_SWIGLU) {        // 32-byte rows per plane either way: always the narrow staging
