@@ -15,7 +15,7 @@
 //        token SwiGLU 28.9 -> 26.4 us, token w2 21.0 -> 19.7 us, token out-proj (K = N = 512: 384 instead of 512 KB of
 //        operands per CTA) 10.5 -> 10.2 us at B = 16 and 9.7 -> 8.8 us at 4 samples of 64 tokens; the K = 128 atom shapes
 //        gain or lose a few tenths of a microsecond (atom out-proj always loses 0.6: cluster launch / two-CTA handshakes on
-//        tiles with 2 K-steps), so they stay on the single-CTA tiling (profiles/r02_gemm_tiling_policy.txt).
+//        tiles with 2 K-steps): they use pair tiles only when N >= 384 and M >= 16384 (profiles/r02_gemm_tiling_policy.txt).
 //   single CTA: 128 x 128 tiles.
 // Tiles are walked n-fastest so concurrently running CTAs share the A tile in L2.  Roles:
 //   warp 0   : TMA producer: 4 plane tiles [128 rows x 64 halves] per stage, SWIZZLE_128B, ring of 3 stages (single CTA,
@@ -450,7 +450,9 @@ cudaError_t launch_one(const GemmArgs& a, cudaStream_t st) {
     // measurement switches: compile-time false in the release build (common.cuh)
     static const bool allow_pair = !measure_switch("PDK_NO_PAIR");
     static const bool force_pair = measure_switch("PDK_FORCE_PAIR");
-    const bool big = (long long)a.K * a.N >= 250000;       // see the header: the K = 128 atom shapes do not gain from the pair tiling
+    // see the header: of the K = 128 atom shapes only the wide ones at large M gain (atom QKV 16.4 -> 15.8, downscale 17.6 -> 16.8 us
+    // at 32768 rows; +0.2 us at 2048-10240 rows); the atom out-proj (N = 128) always loses
+    const bool big = (long long)a.K * a.N >= 250000 || (a.M >= 16384 && a.N >= 384);
     static const bool allow_wide = !measure_switch("PDK_NO_WIDE");
     const bool pair = allow_pair && a.M % (2 * BM) == 0 && (big || force_pair);
     if constexpr (EPI == EPI_SWIGLU) {        // 32-byte rows per plane either way: always the narrow staging
