@@ -300,7 +300,10 @@ __global__ void __launch_bounds__(256) gather_add_kernel(float* __restrict__ ba,
 }
 
 // AF3DiT.denoise (transformers.py:228-233): x_den = c_skip x_hat + c_out Linear_{c_a->3}(LN_affine(ba)).
-// Warp per atom row (c_a = 128: one float4 per lane).
+// A warp takes EIGHT atom rows at a time (c_a = 128: one float4 per lane and row): the eight loads are in flight together and the
+// five row reductions (mean, variance, three output dots) go through the multi-value butterfly, 85 shuffles per 8 rows instead of
+// 200 -- one row per warp with five dependent butterflies was pure latency (12.7 us for 16.8 MB).
+constexpr int kDenoiseRows = 8;
 __global__ void __launch_bounds__(256) denoise_out_kernel(const float* __restrict__ ba, const float* __restrict__ x_hat,
                                                           const float* __restrict__ coef, const float* __restrict__ ln_w,
                                                           const float* __restrict__ ln_b, const float* __restrict__ wr,
@@ -308,29 +311,57 @@ __global__ void __launch_bounds__(256) denoise_out_kernel(const float* __restric
                                                           float eps, int coef_stride, float* __restrict__ x_next) {
     griddep_launch();
     griddep_wait();
-    const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
-    if (r >= B * Na) return;
-    const int b = r / Na, s = r % Na;
-    float4 v = reinterpret_cast<const float4*>(ba + ((size_t)b * S_pad + s) * 128)[lane];
-    const float mean = warp_sum(v.x + v.y + v.z + v.w) * (1.f / 128.f);
-    v.x -= mean; v.y -= mean; v.z -= mean; v.w -= mean;
-    const float rstd = inv_sqrt(warp_sum(v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w) * (1.f / 128.f) + eps);
+    const int rows = B * Na;
+    const int r0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * kDenoiseRows;
+    if (r0 >= rows) return;
+    float4 v[kDenoiseRows];
+    float red[kDenoiseRows];
+#pragma unroll
+    for (int i = 0; i < kDenoiseRows; ++i) {
+        const int r = min(r0 + i, rows - 1);              // the tail warp recomputes the last row (never stored twice)
+        const int b = r / Na, s = r - b * Na;
+        v[i] = reinterpret_cast<const float4*>(ba + ((size_t)b * S_pad + s) * 128)[lane];
+        red[i] = (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    warp_sum8(red);
+#pragma unroll
+    for (int i = 0; i < kDenoiseRows; ++i) {
+        const float mean = red[i] * (1.f / 128.f);
+        v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+        red[i] = fmaf(v[i].x, v[i].x, v[i].y * v[i].y) + fmaf(v[i].z, v[i].z, v[i].w * v[i].w);
+    }
+    warp_sum8(red);
     const float4 g = reinterpret_cast<const float4*>(ln_w)[lane];
     const float4 be = reinterpret_cast<const float4*>(ln_b)[lane];
-    const float y0 = v.x * rstd * g.x + be.x, y1 = v.y * rstd * g.y + be.y;
-    const float y2 = v.z * rstd * g.z + be.z, y3 = v.w * rstd * g.w + be.w;
-    float out[3];
+#pragma unroll
+    for (int i = 0; i < kDenoiseRows; ++i) {
+        const float rstd = inv_sqrt(red[i] * (1.f / 128.f) + eps);
+        v[i].x = v[i].x * rstd * g.x + be.x; v[i].y = v[i].y * rstd * g.y + be.y;
+        v[i].z = v[i].z * rstd * g.z + be.z; v[i].w = v[i].w * rstd * g.w + be.w;
+    }
+    float out[3][kDenoiseRows];
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
         const float4 w = reinterpret_cast<const float4*>(wr + j * 128)[lane];
-        out[j] = warp_sum(fmaf(y3, w.w, fmaf(y2, w.z, fmaf(y1, w.y, y0 * w.x))));
+#pragma unroll
+        for (int i = 0; i < kDenoiseRows; ++i) out[j][i] = fmaf(v[i].w, w.w, fmaf(v[i].z, w.z, fmaf(v[i].y, w.y, v[i].x * w.x)));
+        warp_sum8(out[j]);
     }
-    if (lane < 3) {
+    // lane = 3 * row + component writes one coordinate (24 lanes active)
+    const int i = lane / 3, j = lane - 3 * i;
+    if (lane < 3 * kDenoiseRows && r0 + i < rows) {
+        float r_j = 0.f;
+#pragma unroll
+        for (int jj = 0; jj < 3; ++jj)
+#pragma unroll
+            for (int ii = 0; ii < kDenoiseRows; ++ii)
+                if (jj == j && ii == i) r_j = out[jj][ii];
+        const int r = r0 + i;
+        const int b = r / Na;
         const float* cf = coef + (size_t)coef_stride * b;
         const float c_skip = cf[1], c_out = cf[2];
-        const float r_j = lane == 0 ? out[0] : (lane == 1 ? out[1] : out[2]);
-        const size_t o = ((size_t)b * Na + s) * 3 + lane;
+        const size_t o = (size_t)r * 3 + j;
         const float xh = x_hat[o];
         const float xd = __fadd_rn(__fmul_rn(c_skip, xh), __fmul_rn(c_out, r_j));
         x_den[o] = xd;
@@ -434,7 +465,7 @@ cudaError_t launch_denoise_out(const float* ba, const float* x_hat, const float*
                                const float* ln_b, const float* wr, float* x_den, int B, int Na, int S_pad,
                                int c_a, float eps, float* x_next, cudaStream_t st) {
     if (c_a != 128) return cudaErrorInvalidValue;
-    PDK_LAUNCH_CHECK(launch_pdl(denoise_out_kernel, dim3((B * Na + 7) / 8), dim3(256), (size_t)(0), st, ba, x_hat, coef, ln_w, ln_b, wr, x_den, B, Na, S_pad, eps,
+    PDK_LAUNCH_CHECK(launch_pdl(denoise_out_kernel, dim3((B * Na + 8 * kDenoiseRows - 1) / (8 * kDenoiseRows)), dim3(256), (size_t)(0), st, ba, x_hat, coef, ln_w, ln_b, wr, x_den, B, Na, S_pad, eps,
                                 coef_stride, x_next));
     return cudaGetLastError();
 }
